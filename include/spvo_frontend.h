@@ -1,0 +1,170 @@
+/* spvo_frontend.h -- C ABI of libspvo_frontend.so: B200-native (sm_100a) SuperPoint decode +
+ * brute-force L2 descriptor matching, the data-parallel front end of
+ * YukunXia/SuperPoint-Stereo-Visual-Odometry.
+ *
+ * Every entry point states the reference interface it replaces.  Citations are relative to
+ * /root/reference/src/odml_visual_odometry/ :
+ *   HPP  = include/odml_visual_odometry/feature_detection.hpp
+ *   NN   = src/feature_detection_neural_network.cpp
+ *   BASE = src/feature_detection_base.cpp
+ *
+ * Plain C: opaque handle, raw pointers, sizes, int status codes.  No torch / OpenCV / C++ types.
+ * There is NO CPU fallback behind this ABI: every compute entry point runs hand-written CUDA
+ * kernels and fails with SPVO_ECUDA / SPVO_ENODEVICE when no sm_100 device is usable.
+ *
+ * Threading (as the reference, BASE/NN hold no locks): a handle is not thread-safe; distinct
+ * handles (one per GPU / stream) are fully independent; the library has no global state.
+ */
+#ifndef SPVO_FRONTEND_H_
+#define SPVO_FRONTEND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPVO_ABI_VERSION 1
+
+#define SPVO_DESC_DIM 256      /* output_desc_channel_, HPP:359 */
+#define SPVO_DET_CHANNELS 65   /* output_det_channel_,  HPP:355 */
+#define SPVO_CELL 8            /* output_det_heatmap_factor_, HPP:356 */
+
+/* ---- status codes (the reference logs ROS_ERROR and returns, NN:53-55/489-491; OpenCV throws) ---- */
+enum {
+  SPVO_OK = 0,
+  SPVO_EINVAL = 1,     /* bad argument (null pointer, H or W not a multiple of 8 as HPP:296, size above handle capacity) */
+  SPVO_ECUDA = 2,      /* a CUDA runtime call or kernel failed; see spvo_last_error() */
+  SPVO_ENODEVICE = 3,  /* no usable sm_100 device */
+  SPVO_ENOMEM = 4      /* workspace allocation failed */
+};
+
+/* Layout-compatible with cv::KeyPoint (28 bytes).  The reference emits
+ * cv::KeyPoint(pt=(x,y), size=1) => angle=-1, response=0, octave=0, class_id=-1 (NN:243). */
+typedef struct spvo_keypoint {
+  float x, y;
+  float size;
+  float angle;
+  float response;
+  int32_t octave;
+  int32_t class_id;
+} spvo_keypoint;
+
+/* Layout-compatible with cv::DMatch (16 bytes): the element type of cv_DMatches_list (HPP:129). */
+typedef struct spvo_dmatch {
+  int32_t queryIdx;
+  int32_t trainIdx;
+  int32_t imgIdx; /* always 0, as cv::BFMatcher::match with one train image */
+  float distance; /* sqrt(sum (a-b)^2) with cv::hal::normL2Sqr_'s fp32 operation order */
+} spvo_dmatch;
+
+/* Decode parameters: the SuperPointFeatureFrontEnd members conf_thresh_, dist_thresh_,
+ * border_remove_ (HPP:365-367, launch defaults 0.015 / 4 / 4) and max_keypoints_ (HPP:368, the
+ * compile-time 1000 made a runtime value). */
+typedef struct spvo_decode_cfg {
+  float conf_thresh;
+  int32_t dist_thresh;
+  int32_t border_remove;
+  int32_t max_keypoints;
+} spvo_decode_cfg;
+
+/* Matching modes: SelectorType x cross_check_ as combined in initMatcher (BASE:27-28). */
+enum {
+  SPVO_MATCH_NN = 0,            /* selector NN, crossCheck=false : BFMatcher::match               (BASE:463) */
+  SPVO_MATCH_NN_CROSSCHECK = 1, /* selector NN, crossCheck=true  : mutual first-argmin            (BASE:463) */
+  SPVO_MATCH_KNN_RATIO = 2      /* selector KNN: knnMatch(k=2), keep m0 iff m0.d < ratio * m1.d   (BASE:466-472) */
+};
+
+/* Matcher algorithm inside the library (results are identical; the exact kernel is the anchor). */
+enum {
+  SPVO_MATCHER_AUTO = 0,
+  SPVO_MATCHER_EXACT_FP32 = 1, /* CUDA-core kernel computing every distance in OpenCV's fp32 order */
+  SPVO_MATCHER_TENSOR = 2      /* tcgen05/TMEM bf16 GEMM shortlist + exact fp32 re-rank */
+};
+
+typedef struct spvo_match_cfg {
+  int32_t mode;      /* SPVO_MATCH_* */
+  float ratio;       /* knn_threshold_ = 0.8f (HPP:137); used by SPVO_MATCH_KNN_RATIO */
+  int32_t algorithm; /* SPVO_MATCHER_* */
+  int32_t reserved;
+} spvo_match_cfg;
+
+typedef struct spvo_handle_s* spvo_handle;
+
+/* ---- lifecycle: replaces the SuperPointFeatureFrontEnd ctor's initPointers()/initMatcher()
+ * (HPP:302-318, BASE:10-33) and the dtor (NN:24-41).  The library owns its workspaces; the caller
+ * owns every input and output buffer. ---- */
+int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int max_width,
+                int max_keypoints);
+int spvo_destroy(spvo_handle h);
+const char* spvo_last_error(spvo_handle h); /* h may be NULL: returns the last create error */
+int spvo_abi_version(void);
+
+/* Stream the handle's *_device entry points enqueue on (a cudaStream_t; NULL = the handle's own
+ * stream created at spvo_create, the analogue of NN:134's stream_). */
+int spvo_set_stream(spvo_handle h, void* cuda_stream);
+int spvo_sync(spvo_handle h);
+
+/* ---- decode: replaces SuperPointFeatureFrontEnd::postprocessDetectionAndDescription()
+ * (HPP:327, NN:264-364) including processOneHeatmap (NN:188-262) and bilinearInterpolationDesc
+ * (NN:366-431).
+ *   semi  [B,65,H/8,W/8]  fp32 NCHW  = output_det_data_  (HPP:383)
+ *   desc  [B,256,H/8,W/8] fp32 NCHW  = output_desc_data_ (HPP:384)
+ *   kpts_out [B,K] (K = cfg->max_keypoints), rows beyond n_out[b] are zero-filled
+ *   desc_out [B,K,256] fp32 row-major = the cv::Mat(K,256,CV_32FC1) of NN:347-362
+ *   n_out    [B]  keypoints per image (= keypoints_dq entry sizes)
+ *   scores_out [B,K] optional (may be NULL): heatmap value of each keypoint (the reference drops it)
+ * Host-pointer form: pageable or pinned host memory; copies in, runs, copies out, synchronises. */
+int spvo_decode(spvo_handle h, const float* semi, const float* desc, int B, int H, int W,
+                const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                float* scores_out);
+/* Device-pointer form: all pointers are device memory; asynchronous on the handle's stream. */
+int spvo_decode_device(spvo_handle h, const float* semi, const float* desc, int B, int H, int W,
+                       const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out,
+                       int* n_out, float* scores_out);
+
+/* ---- match: replaces FeatureFrontEnd::matchDescriptors(MatchType) (HPP:118, BASE:434-500),
+ * i.e. cv::BFMatcher(NORM_L2)::match / knnMatch + ratio test, and the index map of BASE:483-491.
+ *   q [N,dim], t [M,dim] fp32 row-major (CV_32F continuous cv::Mat); dim must be 256
+ *   out [>=N] DMatch list in ascending queryIdx; *n_matches entries are valid
+ *   q2t [N] optional: trainIdx per query or -1  (maps_of_indices[type], HPP:161)
+ * Defined edge cases (reference: cv::Exception / UB at BASE:469): N==0 or M==0 -> 0 matches;
+ * KNN_RATIO with M<2 -> 0 matches. */
+int spvo_match(spvo_handle h, const float* q, int N, const float* t, int M, int dim,
+               const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t);
+/* Device-pointer form; n_matches is a device int; asynchronous. */
+int spvo_match_device(spvo_handle h, const float* q, int N, const float* t, int M, int dim,
+                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t);
+
+/* Batched device form: P independent problems per launch (frames are independent in the front
+ * end, so a stream of stereo pairs becomes grouped launches).  Problem p matches
+ *   q = desc_base + q_slot[p]*slot_stride   (n_rows[q_slot[p]] rows)   against
+ *   t = desc_base + t_slot[p]*slot_stride   (n_rows[t_slot[p]] rows)
+ * where a "slot" is one image's [K,256] descriptor block as written by spvo_decode_device and
+ * n_rows is its n_out array (read on the device: no host round trip between decode and match).
+ *   out [P, max_rows] DMatch, n_matches [P], q2t [P, max_rows]. */
+int spvo_match_batch_device(spvo_handle h, const float* desc_base, const int* n_rows, int slot_stride_rows,
+                            const int* q_slot, const int* t_slot, int P, int max_rows, int dim,
+                            const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t);
+
+/* ---- stereo row-band / min-disparity test applied to L<->R matches (BASE:169-172):
+ * keep[m] = !(|y_l - y_r| > stereo_threshold || |x_l - x_r| < min_disparity).
+ * Device form, batched like spvo_match_batch_device (kpts_base slots of slot_stride_rows rows). */
+int spvo_stereo_filter_batch_device(spvo_handle h, const spvo_keypoint* kpts_base, int slot_stride_rows,
+                                    const int* q_slot, const int* t_slot, int P, int max_rows,
+                                    const spvo_dmatch* matches, const int* n_matches,
+                                    float stereo_threshold, float min_disparity, uint8_t* keep);
+
+/* ---- introspection for tests / bench ---- */
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+long long spvo_kernel_launches(spvo_handle h);
+/* Counters of the last decode / match (device work must be complete: call spvo_sync first):
+ * decode: [0] images that left the histogram fast path (slow exact path taken), match: [1] rows
+ * re-ranked by the exact full-row fallback, [2] candidate pairs re-ranked exactly. */
+int spvo_debug_counters(spvo_handle h, long long* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPVO_FRONTEND_H_ */

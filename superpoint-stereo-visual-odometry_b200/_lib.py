@@ -1,0 +1,76 @@
+"""ctypes declarations for the C ABI in include/spvo_frontend.h.  Fails loudly if the CUDA library
+is missing -- there is no CPU fallback in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspvo_frontend.so")
+
+SPVO_OK, SPVO_EINVAL, SPVO_ECUDA, SPVO_ENODEVICE, SPVO_ENOMEM = 0, 1, 2, 3, 4
+MATCH_NN, MATCH_NN_CROSSCHECK, MATCH_KNN_RATIO = 0, 1, 2
+MATCHER_AUTO, MATCHER_EXACT_FP32, MATCHER_TENSOR = 0, 1, 2
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")])
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16
+
+
+class DecodeCfg(C.Structure):
+    _fields_ = [("conf_thresh", C.c_float), ("dist_thresh", C.c_int32), ("border_remove", C.c_int32),
+                ("max_keypoints", C.c_int32)]
+
+
+class MatchCfg(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ratio", C.c_float), ("algorithm", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/spvo_frontend.h declares (checked by tests/test_abi.py against the header)
+SYMBOLS = [
+    "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
+    "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
+    "spvo_stereo_filter_batch_device", "spvo_kernel_launches", "spvo_debug_counters",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  This package has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.spvo_abi_version.restype = ci
+    L.spvo_last_error.restype = C.c_char_p
+    L.spvo_last_error.argtypes = [vp]
+    L.spvo_create.argtypes = [C.POINTER(vp), ci, ci, ci, ci, ci]
+    L.spvo_destroy.argtypes = [vp]
+    L.spvo_set_stream.argtypes = [vp, vp]
+    L.spvo_sync.argtypes = [vp]
+    dec = [vp, vp, vp, ci, ci, ci, C.POINTER(DecodeCfg), vp, vp, vp, vp]
+    L.spvo_decode.argtypes = dec
+    L.spvo_decode_device.argtypes = dec
+    mat = [vp, vp, ci, vp, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
+    L.spvo_match.argtypes = mat
+    L.spvo_match_device.argtypes = mat
+    L.spvo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
+    L.spvo_stereo_filter_batch_device.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp, vp, cf, cf, vp]
+    L.spvo_kernel_launches.restype = C.c_longlong
+    L.spvo_kernel_launches.argtypes = [vp]
+    L.spvo_debug_counters.argtypes = [vp, vp, ci]
+    for name in ("spvo_create", "spvo_destroy", "spvo_set_stream", "spvo_sync", "spvo_decode", "spvo_decode_device",
+                 "spvo_match", "spvo_match_device", "spvo_match_batch_device", "spvo_stereo_filter_batch_device",
+                 "spvo_debug_counters"):
+        getattr(L, name).restype = ci
+    _lib = L
+    return L

@@ -1,0 +1,327 @@
+// api.cu -- the C ABI of libspvo_frontend.so (see include/spvo_frontend.h for the reference
+// interface each entry point replaces).  Host C++ only: argument validation, workspace ownership,
+// stream plumbing, host<->device staging for the host-pointer entry points.  No CPU compute path.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace spvo {
+size_t decode_smem_required(int H, int W, int K);
+}
+
+using namespace spvo;
+
+static char g_create_err[512] = "";
+
+static int fail(Handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(Handle* h, cudaError_t e, const char* what) {
+  return fail(h, SPVO_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                                   \
+  do {                                                             \
+    cudaError_t e_ = (call);                                       \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);         \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+extern "C" {
+
+int spvo_abi_version(void) { return SPVO_ABI_VERSION; }
+
+const char* spvo_last_error(spvo_handle hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  return h ? h->err : g_create_err;
+}
+
+int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int max_width, int max_keypoints) {
+  Handle* h = nullptr;
+  if (!out) return fail(nullptr, SPVO_EINVAL, "spvo_create: out is NULL");
+  *out = nullptr;
+  if (max_batch <= 0 || max_height <= 0 || max_width <= 0 || max_keypoints < 0 || max_height % 8 || max_width % 8)
+    return fail(nullptr, SPVO_EINVAL, "spvo_create: bad capacity (batch %d, %dx%d, K %d; H and W must be multiples of 8)",
+                max_batch, max_height, max_width, max_keypoints);
+  if (max_keypoints > 4096) return fail(nullptr, SPVO_EINVAL, "spvo_create: max_keypoints %d > 4096", max_keypoints);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SPVO_ENODEVICE, "spvo_create: no CUDA device (%s)", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, SPVO_EINVAL, "spvo_create: device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, SPVO_ENODEVICE, "spvo_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  const size_t smem = decode_smem_required(max_height, max_width, max_keypoints > 0 ? max_keypoints : 1);
+  if (smem > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(nullptr, SPVO_EINVAL, "spvo_create: %dx%d with K=%d needs %zu B of shared memory (> %zu)", max_height,
+                max_width, max_keypoints, smem, (size_t)prop.sharedMemPerBlockOptin);
+  h = new (std::nothrow) Handle();
+  if (!h) return fail(nullptr, SPVO_ENOMEM, "spvo_create: out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->max_batch = max_batch; h->max_h = max_height; h->max_w = max_width; h->max_k = max_keypoints;
+  DeviceGuard g(device);
+  const size_t px = (size_t)max_height * max_width, cells = px / 64;
+#define ALLOC(ptr, bytes)                                                         \
+  if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) {                  \
+    int rc = fail(nullptr, SPVO_ENOMEM, "spvo_create: cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); \
+    spvo_destroy(reinterpret_cast<spvo_handle>(h));                                \
+    return rc;                                                                     \
+  }
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "cudaStreamCreate");
+    delete h;
+    return rc;
+  }
+  h->stream = h->own_stream;
+  ALLOC(h->heat, (size_t)max_batch * px * sizeof(float));
+  ALLOC(h->hist, (size_t)max_batch * kHistBins * sizeof(unsigned));
+  ALLOC(h->counters, 8 * sizeof(unsigned long long));
+  cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long));
+  const size_t K = max_keypoints > 0 ? max_keypoints : 1;
+  ALLOC(h->st_semi, (size_t)max_batch * 65 * cells * sizeof(float));
+  ALLOC(h->st_desc, (size_t)max_batch * 256 * cells * sizeof(float));
+  ALLOC(h->st_kpts, (size_t)max_batch * K * sizeof(spvo_keypoint));
+  ALLOC(h->st_desc_out, (size_t)max_batch * K * 256 * sizeof(float));
+  ALLOC(h->st_n, (size_t)max_batch * sizeof(int));
+  ALLOC(h->st_scores, (size_t)max_batch * K * sizeof(float));
+  ALLOC(h->probs, 4096 * sizeof(MatchProblem));
+  h->probs_cap = 4096;
+#undef ALLOC
+  *out = reinterpret_cast<spvo_handle>(h);
+  return SPVO_OK;
+}
+
+int spvo_destroy(spvo_handle hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_OK;
+  DeviceGuard g(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  void* ptrs[] = {h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+                  h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
+                  h->st_matches, h->st_q2t, h->st_nm};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return SPVO_OK;
+}
+
+int spvo_set_stream(spvo_handle hh, void* cuda_stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return SPVO_OK;
+}
+
+int spvo_sync(spvo_handle hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return SPVO_OK;
+}
+
+static int check_decode_args(Handle* h, const float* semi, int B, int H, int W, const spvo_decode_cfg* cfg,
+                             spvo_keypoint* kpts, int* n_out) {
+  if (!h) return SPVO_EINVAL;
+  if (!semi || !cfg || !kpts || !n_out) return fail(h, SPVO_EINVAL, "decode: NULL argument");
+  if (B < 0 || B > h->max_batch) return fail(h, SPVO_EINVAL, "decode: batch %d outside [0, %d]", B, h->max_batch);
+  if (H <= 0 || W <= 0 || H % 8 || W % 8)
+    return fail(h, SPVO_EINVAL, "decode: %dx%d is not a positive multiple of 8 (reference: feature_detection.hpp:296)", H, W);
+  if ((size_t)H * W > (size_t)h->max_h * h->max_w)
+    return fail(h, SPVO_EINVAL, "decode: %dx%d exceeds the handle capacity %dx%d", H, W, h->max_h, h->max_w);
+  if (H < 16 || W < 16) return fail(h, SPVO_EINVAL, "decode: image smaller than 16x16");
+  if (cfg->max_keypoints < 0 || cfg->max_keypoints > h->max_k)
+    return fail(h, SPVO_EINVAL, "decode: max_keypoints %d outside [0, %d]", cfg->max_keypoints, h->max_k);
+  if (cfg->dist_thresh < 0 || cfg->dist_thresh > 64 || cfg->border_remove < 0 || !(cfg->conf_thresh >= 0.0f))
+    return fail(h, SPVO_EINVAL, "decode: bad cfg (conf %g, dist %d, border %d)", (double)cfg->conf_thresh,
+                cfg->dist_thresh, cfg->border_remove);
+  return SPVO_OK;
+}
+
+int spvo_decode_device(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
+                       const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                       float* scores_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_decode_args(h, semi, B, H, W, cfg, kpts_out, n_out);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  CK(launch_decode(h, semi, desc, B, H, W, *cfg, kpts_out, desc_out, n_out, scores_out));
+  return SPVO_OK;
+}
+
+int spvo_decode(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
+                const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                float* scores_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_decode_args(h, semi, B, H, W, cfg, kpts_out, n_out);
+  if (rc) return rc;
+  if (B == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const size_t cells = (size_t)(H / 8) * (W / 8), K = cfg->max_keypoints;
+  const bool with_desc = desc && desc_out;
+  CK(cudaMemcpyAsync(h->st_semi, semi, (size_t)B * 65 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (with_desc)
+    CK(cudaMemcpyAsync(h->st_desc, desc, (size_t)B * 256 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(launch_decode(h, h->st_semi, with_desc ? h->st_desc : nullptr, B, H, W, *cfg, h->st_kpts,
+                   with_desc ? h->st_desc_out : nullptr, h->st_n, scores_out ? h->st_scores : nullptr));
+  CK(cudaMemcpyAsync(n_out, h->st_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (K > 0) {
+    CK(cudaMemcpyAsync(kpts_out, h->st_kpts, (size_t)B * K * sizeof(spvo_keypoint), cudaMemcpyDeviceToHost, st));
+    if (with_desc)
+      CK(cudaMemcpyAsync(desc_out, h->st_desc_out, (size_t)B * K * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (scores_out)
+      CK(cudaMemcpyAsync(scores_out, h->st_scores, (size_t)B * K * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return SPVO_OK;
+}
+
+static int check_match_cfg(Handle* h, const spvo_match_cfg* cfg, int dim) {
+  if (!cfg) return fail(h, SPVO_EINVAL, "match: cfg is NULL");
+  if (dim != SPVO_DESC_DIM) return fail(h, SPVO_EINVAL, "match: dim %d unsupported (SuperPoint descriptors are 256-d)", dim);
+  if (cfg->mode < SPVO_MATCH_NN || cfg->mode > SPVO_MATCH_KNN_RATIO) return fail(h, SPVO_EINVAL, "match: mode %d", cfg->mode);
+  if (cfg->algorithm < SPVO_MATCHER_AUTO || cfg->algorithm > SPVO_MATCHER_TENSOR)
+    return fail(h, SPVO_EINVAL, "match: algorithm %d", cfg->algorithm);
+  return SPVO_OK;
+}
+
+static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                     const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride) {
+  // SPVO_MATCHER_TENSOR is dispatched here once the tcgen05 path lands; AUTO = exact for now.
+  CK(launch_match_exact(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
+  return SPVO_OK;
+}
+
+int spvo_match_device(spvo_handle hh, const float* q, int N, const float* t, int M, int dim,
+                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  int rc = check_match_cfg(h, cfg, dim);
+  if (rc) return rc;
+  if (N < 0 || M < 0 || !n_matches || (N > 0 && (!q || !out)) || (M > 0 && !t))
+    return fail(h, SPVO_EINVAL, "match: bad arguments (N %d, M %d)", N, M);
+  DeviceGuard g(h->device);
+  CK(launch_set_problem(h, h->probs, q, N, t, M));
+  return run_match(h, h->probs, 1, N, M, cfg, out, n_matches, q2t, N > 0 ? N : 1);
+}
+
+int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
+               spvo_dmatch* out, int* n_matches, int* q2t) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  int rc = check_match_cfg(h, cfg, dim);
+  if (rc) return rc;
+  if (N < 0 || M < 0 || !n_matches || (N > 0 && (!q || !out)) || (M > 0 && !t))
+    return fail(h, SPVO_EINVAL, "match: bad arguments (N %d, M %d)", N, M);
+  *n_matches = 0;
+  if (N == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const size_t rows = (size_t)(N > M ? N : M);
+  if (h->st_rows < rows) {
+    void** ps[] = {(void**)&h->st_q, (void**)&h->st_t, (void**)&h->st_matches, (void**)&h->st_q2t, (void**)&h->st_nm};
+    for (void** p : ps) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    h->st_rows = 0;
+    CK(cudaMalloc((void**)&h->st_q, rows * 256 * sizeof(float)));
+    CK(cudaMalloc((void**)&h->st_t, rows * 256 * sizeof(float)));
+    CK(cudaMalloc((void**)&h->st_matches, rows * sizeof(spvo_dmatch)));
+    CK(cudaMalloc((void**)&h->st_q2t, rows * sizeof(int)));
+    CK(cudaMalloc((void**)&h->st_nm, sizeof(int)));
+    h->st_rows = rows;
+  }
+  CK(cudaMemcpyAsync(h->st_q, q, (size_t)N * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (M > 0) CK(cudaMemcpyAsync(h->st_t, t, (size_t)M * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(launch_set_problem(h, h->probs, h->st_q, N, h->st_t, M));
+  rc = run_match(h, h->probs, 1, N, M, cfg, h->st_matches, h->st_nm, h->st_q2t, N);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(n_matches, h->st_nm, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (q2t) CK(cudaMemcpyAsync(q2t, h->st_q2t, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (*n_matches > 0)
+    CK(cudaMemcpy(out, h->st_matches, (size_t)*n_matches * sizeof(spvo_dmatch), cudaMemcpyDeviceToHost));
+  return SPVO_OK;
+}
+
+int spvo_match_batch_device(spvo_handle hh, const float* desc_base, const int* n_rows, int slot_stride_rows,
+                            const int* q_slot, const int* t_slot, int P, int max_rows, int dim,
+                            const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  int rc = check_match_cfg(h, cfg, dim);
+  if (rc) return rc;
+  if (P < 0 || max_rows < 0 || slot_stride_rows < max_rows || !desc_base || !n_rows || !q_slot || !t_slot || !out ||
+      !n_matches)
+    return fail(h, SPVO_EINVAL, "match_batch: bad arguments (P %d, max_rows %d, stride %d)", P, max_rows, slot_stride_rows);
+  if (P == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  if (P > h->probs_cap) {
+    cudaFree(h->probs);
+    h->probs = nullptr;
+    h->probs_cap = 0;
+    CK(cudaMalloc((void**)&h->probs, (size_t)P * sizeof(MatchProblem)));
+    h->probs_cap = P;
+  }
+  CK(launch_setup_problems(h, h->probs, desc_base, n_rows, slot_stride_rows, q_slot, t_slot, P));
+  return run_match(h, h->probs, P, max_rows, max_rows, cfg, out, n_matches, q2t, max_rows > 0 ? max_rows : 1);
+}
+
+int spvo_stereo_filter_batch_device(spvo_handle hh, const spvo_keypoint* kpts_base, int slot_stride_rows,
+                                    const int* q_slot, const int* t_slot, int P, int max_rows,
+                                    const spvo_dmatch* matches, const int* n_matches, float stereo_threshold,
+                                    float min_disparity, uint8_t* keep) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  if (P < 0 || max_rows < 0 || !kpts_base || !q_slot || !t_slot || !matches || !n_matches || !keep)
+    return fail(h, SPVO_EINVAL, "stereo_filter: bad arguments");
+  DeviceGuard g(h->device);
+  CK(launch_stereo_filter(h, kpts_base, slot_stride_rows, q_slot, t_slot, P, max_rows, matches, n_matches,
+                          stereo_threshold, min_disparity, keep));
+  return SPVO_OK;
+}
+
+long long spvo_kernel_launches(spvo_handle hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  return h ? h->launches : -1;
+}
+
+int spvo_debug_counters(spvo_handle hh, long long* out, int n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !out || n < 0) return SPVO_EINVAL;
+  DeviceGuard g(h->device);
+  unsigned long long c[8];
+  CK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n && i < 8; ++i) out[i] = (long long)c[i];
+  return SPVO_OK;
+}
+
+}  // extern "C"

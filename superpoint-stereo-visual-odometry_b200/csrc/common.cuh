@@ -1,0 +1,102 @@
+// common.cuh -- shared declarations for libspvo_frontend.so (sm_100a only).
+// Compiled with -fmad=false: every fp32 operation is a single IEEE round-to-nearest op in source
+// order unless an explicit __fmaf_rn is written, so results match oracle/spvo_oracle.cpp bit for bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "spvo_frontend.h"
+
+namespace spvo {
+
+// Sampled score histogram used to pick the first candidate chunk (decode.cu).
+// bin(v) = (bits(1.0f) - bits(v)) >> 14, clamped to [0, 4095]; bin 0 holds the highest scores.
+constexpr int kHistBins = 4096;
+constexpr int kHistShift = 14;
+constexpr uint32_t kOneBits = 0x3F800000u;
+
+struct Handle;
+
+// One matching problem, resident on the device (built by k_setup_problems / k_set_problem).
+struct MatchProblem {
+  const float* q;  // [N,256]
+  const float* t;  // [M,256]
+  int N, M;
+};
+
+// ---- decode.cu ----
+cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
+                          const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
+                          float* scores);
+// ---- match.cu ----
+cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                               const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
+                               int out_stride);
+cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
+                                  int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
+cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
+cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
+                                 const int* q_slot, const int* t_slot, int P, int max_rows,
+                                 const spvo_dmatch* matches, const int* n_matches, float stereo_threshold,
+                                 float min_disparity, uint8_t* keep);
+
+struct Handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int max_batch = 0, max_h = 0, max_w = 0, max_k = 0;
+  // decode workspace
+  float* heat = nullptr;          // [max_batch, max_h*max_w]
+  unsigned* hist = nullptr;       // [max_batch, kHistBins]
+  unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)
+  // staging for the host-pointer entry points
+  float* st_semi = nullptr;
+  float* st_desc = nullptr;
+  spvo_keypoint* st_kpts = nullptr;
+  float* st_desc_out = nullptr;
+  int* st_n = nullptr;
+  float* st_scores = nullptr;
+  // matching workspace (grown on demand)
+  float* dist = nullptr;
+  size_t dist_elems = 0;
+  int* row_best = nullptr;   // [P*max_rows*2] best / second-best train index per query
+  float* row_d = nullptr;    // [P*max_rows*2]
+  int* col_best = nullptr;   // [P*max_cols]
+  size_t sel_rows = 0, sel_cols = 0;
+  MatchProblem* probs = nullptr;
+  int probs_cap = 0;
+  float* st_q = nullptr;
+  float* st_t = nullptr;
+  spvo_dmatch* st_matches = nullptr;
+  int* st_q2t = nullptr;
+  int* st_nm = nullptr;
+  size_t st_rows = 0;
+  long long launches = 0;
+  char err[512] = {0};
+};
+
+__device__ __forceinline__ uint32_t fbits(float f) { return __float_as_uint(f); }
+
+// exp as specified by the oracle (oracle/spvo_oracle.cpp: oracle_exp): Cephes/Eigen-style expf
+// written as explicit IEEE fp32 operations.  Replaces Eigen's packet exp at NN:271.
+__device__ __forceinline__ float spvo_exp(float x0) {
+  float x = fminf(fmaxf(x0, -88.3762626647949f), 88.3762626647950f);
+  float m = floorf(__fmaf_rn(x, 1.44269504088896341f, 0.5f));
+  float r = __fmaf_rn(m, -0.6931471805599453f, x);
+  float r2 = __fmul_rn(r, r);
+  float y = 1.9875691500E-4f;
+  y = __fmaf_rn(y, r, 1.3981999507E-3f);
+  y = __fmaf_rn(y, r, 8.3334519073E-3f);
+  y = __fmaf_rn(y, r, 4.1665795894E-2f);
+  y = __fmaf_rn(y, r, 1.6666665459E-1f);
+  y = __fmaf_rn(y, r, 5.0000001201E-1f);
+  y = __fmaf_rn(y, r2, r);
+  y = __fadd_rn(y, 1.0f);
+  int e = (int)m + 127;
+  float scale = __uint_as_float((uint32_t)e << 23);
+  return fmaxf(__fmul_rn(y, scale), x0);
+}
+
+}  // namespace spvo

@@ -1,0 +1,521 @@
+// decode.cu -- SuperPoint decode kernels (sm_100a).
+//
+// Replaces SuperPointFeatureFrontEnd::postprocessDetectionAndDescription() and its helpers
+// (reference: src/odml_visual_odometry/src/feature_detection_neural_network.cpp, "NN" below):
+//   k_softmax_heat  NN:266-326  exp, channel sum (c = 0..64 in order), /(sum + 1e-5), dustbin drop,
+//                               depth-to-space to the H x W heatmap; plus a sampled score histogram.
+//   k_detect        NN:188-262  strict '>' threshold, descending-score order with the canonical
+//                               tie-break (score desc, x asc, y asc), greedy box NMS, border filter,
+//                               stop at K emitted.  Exact: candidates are consumed in descending key
+//                               order chunk by chunk, so the result equals a full sort + sequential walk.
+//   k_sample_desc   NN:332-431  align-corners bilinear sampling of the coarse 256-d map + L2 normalise.
+//
+// HBM-bound integer/float streaming work: coalesced 128 B channel-plane reads of semi, 32 B-aligned
+// float4 heatmap stores, warp-shuffle reductions; no tensor cores here.
+#include "common.cuh"
+
+namespace spvo {
+
+// ------------------------------------------------------------------------------------------------
+// K1: softmax + heatmap.  Block = 256 threads = 32 consecutive cells x 8 heatmap rows.
+//   thread (grp = warp id, lane): cell = 32*blockIdx.x + lane, channels 8*grp .. 8*grp+7
+//   -> every global load is one 128 B coalesced request per warp (channel plane, consecutive cells)
+//   -> every warp stores 32 cells x 32 B = 1 KB contiguous of heatmap row 8*hc + grp.
+// The 65-term channel sum must be accumulated in channel order (oracle: s = s + e_c, c = 0..64), so
+// the exps go through shared memory and warp 0 does the ordered sum for the block's 32 cells.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
+               int Hc, int Wc, float conf) {
+  __shared__ float e_s[65][32];
+  __shared__ float denom_s[32];
+  const int b = blockIdx.y;
+  const int cells = Hc * Wc;
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int cell = blockIdx.x * 32 + lane;
+  const bool valid = cell < cells;
+  const float* src = semi + (size_t)b * 65 * cells + cell;
+  float e[8];
+  if (valid) {
+    float xin[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xin[j] = __ldg(src + (size_t)(8 * grp + j) * cells);
+    float xd = 0.f;
+    if (grp == 1) xd = __ldg(src + (size_t)64 * cells);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      e[j] = spvo_exp(xin[j]);
+      e_s[8 * grp + j][lane] = e[j];
+    }
+    if (grp == 1) e_s[64][lane] = spvo_exp(xd);
+  }
+  __syncthreads();
+  if (grp == 0 && valid) {
+    float s = 0.0f;
+#pragma unroll 13
+    for (int c = 0; c < 65; ++c) s = __fadd_rn(s, e_s[c][lane]);
+    denom_s[lane] = __fadd_rn(s, 0.00001f);
+  }
+  __syncthreads();
+  if (!valid) return;
+  const float denom = denom_s[lane];
+  float p[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = __fdiv_rn(e[j], denom);
+  const int hc = cell / Wc, wc = cell - hc * Wc;
+  const int W = Wc * 8;
+  float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc + grp) * W + 8 * wc;
+  reinterpret_cast<float4*>(dst)[0] = make_float4(p[0], p[1], p[2], p[3]);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(p[4], p[5], p[6], p[7]);
+  // Sampled histogram: one pixel per (cell, row) on a diagonal -> 8 of the cell's 64 pixels.
+  // Only used to ESTIMATE the first chunk's score threshold; exactness never depends on it.
+  const int js = (grp + cell) & 7;
+  float v = p[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) v = (j == js) ? p[j] : v;
+  if (v > conf) {
+    uint32_t bits = fbits(v);
+    uint32_t bin = bits >= kOneBits ? 0u : min((kOneBits - bits) >> kHistShift, (uint32_t)(kHistBins - 1));
+    atomicAdd(&hist[(size_t)b * kHistBins + bin], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-image detect.  One CTA per image.
+// Candidate key (64 bit, unique per pixel): (score_bits << 32) | (0xFFFFFFFF - (x*H + y)).
+// Descending key order == score descending, then x ascending, then y ascending == a stable sort of
+// the reference's column-major candidate list (NN:205-217).
+// ------------------------------------------------------------------------------------------------
+struct DetectParams {
+  const float* heat;
+  const unsigned* hist;
+  int H, W;
+  float conf;
+  int dist, border, K;
+  spvo_keypoint* kpts;
+  float* scores;
+  int* n_out;
+  unsigned long long* counters;
+  int cap;        // key buffer capacity (power of two)
+  int target;     // candidates wanted in the first chunk
+};
+
+constexpr int kDetectThreads = 512;
+typedef unsigned long long u64;
+
+struct Scan {  // running (x, y) of a thread's current float4 while striding over the heatmap
+  int x, y, dx, dy;
+};
+
+__device__ __forceinline__ u64 make_key(uint32_t bits, int x, int y, int H) {
+  return ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
+}
+
+// Visit every pixel of the image once (float4 granularity, uniform trip count per warp).
+// f(bits, x, y) is called for the four pixels of each float4; `any` prefilter keeps the common
+// no-candidate case to one vote.
+template <class Pred, class Fn>
+__device__ __forceinline__ void scan_heat(const float* __restrict__ heat, int H, int W, Pred pred, Fn fn) {
+  const int n4 = (H * W) >> 2;
+  const int S = kDetectThreads * 4;
+  const int dy = S / W, dx = S - dy * W;
+  int p0 = threadIdx.x * 4;
+  int y = p0 / W, x = p0 - y * W;
+  for (int base = 0; base < n4; base += kDetectThreads) {
+    const int i4 = base + threadIdx.x;
+    const bool in = i4 < n4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) v = __ldg(reinterpret_cast<const float4*>(heat) + i4);
+    const uint32_t b0 = fbits(v.x), b1 = fbits(v.y), b2 = fbits(v.z), b3 = fbits(v.w);
+    const bool s0 = in && pred(b0), s1 = in && pred(b1), s2 = in && pred(b2), s3 = in && pred(b3);
+    if (__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) {
+      fn(s0, b0, x, y);
+      fn(s1, b1, x + 1, y);
+      fn(s2, b2, x + 2, y);
+      fn(s3, b3, x + 3, y);
+    }
+    x += dx;
+    y += dy;
+    if (x >= W) {
+      x -= W;
+      ++y;
+    }
+  }
+}
+
+// Collect every key in [lo, hi) into keys[] (first `cap` only); returns the total count.
+__device__ int collect_keys(const float* heat, int H, int W, uint32_t conf_bits, u64 lo, u64 hi, u64* keys,
+                            int cap, int* s_count) {
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
+  const int lane = threadIdx.x & 31;
+  scan_heat(
+      heat, H, W, [&](uint32_t b) { return b > conf_bits && b >= lo_b && b <= hi_b; },
+      [&](bool s, uint32_t b, int x, int y) {
+        u64 key = make_key(b, x, y, H);
+        s = s && key >= lo && key < hi;
+        unsigned m = __ballot_sync(0xffffffffu, s);
+        if (m) {
+          int leader = __ffs(m) - 1, basei = 0;
+          if (lane == leader) basei = atomicAdd(s_count, __popc(m));
+          basei = __shfl_sync(0xffffffffu, basei, leader);
+          if (s) {
+            int slot = basei + __popc(m & ((1u << lane) - 1u));
+            if (slot < cap) keys[slot] = key;
+          }
+        }
+      });
+  __syncthreads();
+  return *s_count;
+}
+
+// Exact radix select: returns the m-th largest key among candidate keys < hi (unique keys), or
+// `floor_key` when fewer than m remain.  8 passes of 8 bits over the heatmap (slow path only).
+__device__ u64 radix_select(const float* heat, int H, int W, uint32_t conf_bits, u64 hi, int m, u64 floor_key,
+                            unsigned* s_hist, u64* s_prefix, int* s_want) {
+  if (threadIdx.x == 0) {
+    *s_prefix = 0;
+    *s_want = m;
+  }
+  const uint32_t hi_b = (uint32_t)(hi >> 32);
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += kDetectThreads) s_hist[i] = 0;
+    __syncthreads();
+    const u64 prefix = *s_prefix;
+    scan_heat(
+        heat, H, W, [&](uint32_t b) { return b > conf_bits && b <= hi_b; },
+        [&](bool s, uint32_t b, int x, int y) {
+          u64 key = make_key(b, x, y, H);
+          s = s && key < hi && (pass == 0 || (key >> (shift + 8)) == prefix);
+          unsigned act = __ballot_sync(0xffffffffu, s);
+          if (s) {
+            unsigned digit = (unsigned)(key >> shift) & 255u;
+            unsigned peers = __match_any_sync(act, digit);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+          }
+        });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int want = *s_want, cum = 0, d = 255;
+      bool found = false;
+      for (; d >= 0; --d) {
+        int c = (int)s_hist[d];
+        if (cum + c >= want) {
+          found = true;
+          break;
+        }
+        cum += c;
+      }
+      if (!found) {
+        *s_want = -1;  // fewer than m keys remain
+      } else {
+        *s_want = want - cum;
+        *s_prefix = (prefix << 8) | (u64)d;
+      }
+    }
+    __syncthreads();
+    if (*s_want < 0) return floor_key;
+  }
+  u64 thr = *s_prefix;
+  return thr < floor_key ? floor_key : thr;
+}
+
+// In-place bitonic sort, descending, n_pad a power of two (padding keys are 0 < any valid key).
+__device__ void bitonic_sort_desc(u64* keys, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += kDetectThreads) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        u64 a = keys[i], c = keys[i + j];
+        bool up = (i & k) == 0;  // descending run
+        if ((a < c) == up) {
+          keys[i] = c;
+          keys[i + j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int H = p.H, W = p.W, K = p.K, cap = p.cap;
+  const int ww = (W + 31) >> 5;  // bitmap words per row
+  u64* keys = reinterpret_cast<u64*>(smem_raw);                  // [cap]
+  u64* emit = keys + cap;                                        // [K]
+  unsigned* bitmap = reinterpret_cast<unsigned*>(emit + K);      // [H*ww]
+  unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (used before collect)
+  __shared__ int s_count, s_want, s_bin, s_emitted;
+  __shared__ u64 s_prefix;
+  __shared__ unsigned s_warp_tot[kDetectThreads / 32];
+
+  const float* heat = p.heat + (size_t)b * H * W;
+  const uint32_t conf_bits = fbits(fmaxf(p.conf, 0.0f));
+  const u64 floor_key = ((u64)conf_bits + 1ull) << 32;  // smallest possible candidate key (score > conf)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- zero the suppression bitmap -------------------------------------------------------------
+  for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
+  if (tid == 0) {
+    s_emitted = 0;
+    s_bin = kHistBins - 1;
+  }
+
+  // ---- first-chunk threshold from the sampled histogram (estimate only) ------------------------
+  {
+    const unsigned* hist = p.hist + (size_t)b * kHistBins;
+    constexpr int per = kHistBins / kDetectThreads;
+    unsigned loc[per], sum = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+      loc[i] = hist[tid * per + i];
+      sum += loc[i];
+    }
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned off = 0;
+    for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+    const unsigned excl = off + inc - sum;
+    const unsigned want = (unsigned)((p.target + 7) / 8);  // histogram holds 1 of every 8 pixels
+    if (excl < want && excl + sum >= want) {
+      unsigned c = excl;
+      for (int i = 0; i < per; ++i) {
+        c += loc[i];
+        if (c >= want) {
+          s_bin = tid * per + i;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  u64 hi = ~0ull;
+  u64 lo;
+  {
+    const int bin = s_bin;
+    // bin(v) <= bin  <=>  bits > kOneBits - ((bin+1) << shift)
+    if (bin >= kHistBins - 1) {
+      lo = floor_key;
+    } else {
+      uint32_t tb = kOneBits - ((uint32_t)(bin + 1) << kHistShift);
+      lo = ((u64)tb + 1ull) << 32;
+      if (lo < floor_key) lo = floor_key;
+    }
+  }
+  __syncthreads();  // s_hist (aliasing keys) no longer needed
+
+  bool slow = false;
+  // ---- chunk loop: consume candidates in descending key order ----------------------------------
+  while (true) {
+    int n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
+    if (n > cap) {  // estimate too generous (or heavy ties): shrink the chunk exactly
+      slow = true;
+      __syncthreads();
+      lo = radix_select(heat, H, W, conf_bits, hi, cap, floor_key, s_hist, &s_prefix, &s_want);
+      __syncthreads();
+      n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
+    }
+    int n_pad = 32;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = n + tid; i < n_pad; i += kDetectThreads) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(keys, n_pad);
+
+    // ---- greedy NMS walk (warp 0), 32 candidates per window -------------------------------------
+    if (warp == 0) {
+      int emitted = s_emitted;
+      const int d = p.dist, bd = p.border;
+      for (int base = 0; base < n && emitted < K; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < n;
+        u64 key = valid ? keys[idx] : 0ull;
+        uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
+        int x = valid ? (int)(pos / (uint32_t)H) : -1000000;
+        int y = valid ? (int)(pos - (uint32_t)x * (uint32_t)H) : -1000000;
+        bool supp = !valid;
+        if (valid) supp = (bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u;
+        unsigned alive = __ballot_sync(0xffffffffu, !supp);
+        while (alive && emitted < K) {
+          const int j = __ffs(alive) - 1;
+          const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+          // emit iff inside the border (NN:239-244); a border point still suppresses (NN:246-254)
+          if (yj >= bd && yj + bd < H && xj >= bd && xj + bd < W) {
+            if (lane == j) emit[emitted] = key;
+            ++emitted;
+          }
+          // mark the (2d+1)^2 box, clipped to the image
+          const int x0 = max(xj - d, 0), x1 = min(xj + d, W - 1);
+          for (int r = lane; r < 2 * d + 1; r += 32) {
+            const int yy = yj - d + r;
+            if (yy >= 0 && yy < H) {
+              for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+                const int lo_b = max(x0 - (w << 5), 0), hi_b = min(x1 - (w << 5), 31);
+                const unsigned mask = (0xffffffffu >> (31 - hi_b)) & (0xffffffffu << lo_b);
+                bitmap[yy * ww + w] |= mask;
+              }
+            }
+          }
+          // candidates of this window inside the new box are suppressed (j itself included)
+          if (abs(x - xj) <= d && abs(y - yj) <= d) supp = true;
+          alive = __ballot_sync(0xffffffffu, !supp) & ~((2u << j) - 1u);
+          __syncwarp();  // box marks of this point are visible before the next point's read-modify-write
+        }
+        __syncwarp();
+      }
+      if (lane == 0) s_emitted = emitted;
+    }
+    __syncthreads();
+    if (s_emitted >= K || lo <= floor_key) break;
+    // more candidates are needed: next chunk = the next `cap` keys below lo (exact slow path)
+    slow = true;
+    hi = lo;
+    lo = radix_select(heat, H, W, conf_bits, hi, cap, floor_key, s_hist, &s_prefix, &s_want);
+    __syncthreads();
+  }
+
+  // ---- outputs ---------------------------------------------------------------------------------
+  const int n_emit = min(s_emitted, K);
+  spvo_keypoint* kp = p.kpts + (size_t)b * K;
+  for (int i = tid; i < K; i += kDetectThreads) {
+    spvo_keypoint o;
+    float sc = 0.f;
+    if (i < n_emit) {
+      const u64 key = emit[i];
+      const uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
+      const int x = (int)(pos / (uint32_t)H), y = (int)(pos - (uint32_t)x * (uint32_t)H);
+      o.x = (float)x; o.y = (float)y; o.size = 1.0f; o.angle = -1.0f; o.response = 0.0f;
+      o.octave = 0; o.class_id = -1;
+      sc = __uint_as_float((uint32_t)(key >> 32));
+    } else {
+      o.x = o.y = o.size = o.angle = o.response = 0.0f;
+      o.octave = 0; o.class_id = 0;
+    }
+    kp[i] = o;
+    if (p.scores) p.scores[(size_t)b * K + i] = sc;
+  }
+  if (tid == 0) {
+    p.n_out[b] = n_emit;
+    if (slow) atomicAdd(&p.counters[0], 1ull);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: descriptor sampling.  One warp per keypoint; lane l owns channels l, l+32, ..., l+224.
+// Arithmetic order is the oracle's (sample_descriptor): each term (vec*s1)*s2, summed left to
+// right, unfused; squared norm = per-lane partial sums over ascending channels, xor butterfly
+// 16,8,4,2,1; true division by sqrt.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ kpts, const int* __restrict__ n_out,
+              float* __restrict__ out, int H, int W, int K) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  float* o = out + ((size_t)b * K + k) * 256;
+  if (k >= n_out[b]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[lane + 32 * i] = 0.0f;
+    return;
+  }
+  const int Hc = H >> 3, Wc = W >> 3;
+  const size_t cells = (size_t)Hc * Wc;
+  const spvo_keypoint kp = kpts[(size_t)b * K + k];
+  const int x = (int)kp.x, y = (int)kp.y;
+  const float r8 = __fmul_rn(__fdiv_rn((float)y, (float)(H - 1)), (float)(Hc - 1));
+  const float c8 = __fmul_rn(__fdiv_rn((float)x, (float)(W - 1)), (float)(Wc - 1));
+  const int r0 = (int)floorf(r8), c0 = (int)floorf(c8);
+  const float rr = __fsub_rn(1.0f, __fsub_rn(r8, (float)r0));
+  const float cr = __fsub_rn(1.0f, __fsub_rn(c8, (float)c0));
+  const float irr = __fsub_rn(1.0f, rr), icr = __fsub_rn(1.0f, cr);
+  const int r1 = min(r0 + 1, Hc - 1), c1 = min(c0 + 1, Wc - 1);
+  const float* base = desc + (size_t)b * 256 * cells;
+  const float* tl = base + (size_t)r0 * Wc + c0;
+  const float* tr = base + (size_t)r0 * Wc + c1;
+  const float* bl = base + (size_t)r1 * Wc + c0;
+  const float* br = base + (size_t)r1 * Wc + c1;
+  float a[8], bq[8], c[8], dd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const size_t off = (size_t)(lane + 32 * i) * cells;
+    a[i] = __ldg(tl + off);
+    bq[i] = __ldg(tr + off);
+    c[i] = __ldg(bl + off);
+    dd[i] = __ldg(br + off);
+  }
+  float v[8], part = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float t1 = __fmul_rn(__fmul_rn(a[i], rr), cr);
+    const float t2 = __fmul_rn(__fmul_rn(bq[i], rr), icr);
+    const float t3 = __fmul_rn(__fmul_rn(c[i], irr), cr);
+    const float t4 = __fmul_rn(__fmul_rn(dd[i], irr), icr);
+    v[i] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
+    part = __fadd_rn(part, __fmul_rn(v[i], v[i]));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+  if (part > 0.0f) {
+    const float nrm = __fsqrt_rn(part);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fdiv_rn(v[i], nrm);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[lane + 32 * i] = v[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launcher
+// ------------------------------------------------------------------------------------------------
+static size_t detect_smem_bytes(int H, int W, int K, int cap) {
+  const int ww = (W + 31) >> 5;
+  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4;
+}
+
+cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
+                          const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
+                          float* scores) {
+  cudaStream_t st = h->stream;
+  const int Hc = H / 8, Wc = W / 8, cells = Hc * Wc, K = cfg.max_keypoints;
+  cudaError_t e;
+  if (B == 0) return cudaSuccess;
+  if ((e = cudaMemsetAsync(h->hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
+  dim3 g1((cells + 31) / 32, B);
+  k_softmax_heat<<<g1, 256, 0, st>>>(semi, h->heat, h->hist, Hc, Wc, cfg.conf_thresh);
+  h->launches++;
+  if (K > 0) {
+    DetectParams p;
+    p.heat = h->heat; p.hist = h->hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
+    p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
+    p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
+    p.cap = K <= 1536 ? 4096 : 8192;
+    p.target = min(p.cap * 3 / 4, K + K / 2 + 256);
+    const size_t smem = detect_smem_bytes(H, W, K, p.cap);
+    if ((e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    k_detect<<<B, kDetectThreads, smem, st>>>(p);
+    h->launches++;
+    if (desc && desc_out) {
+      dim3 g3((K + 7) / 8, B);
+      k_sample_desc<<<g3, 256, 0, st>>>(desc, kpts, n_out, desc_out, H, W, K);
+      h->launches++;
+    }
+  } else {
+    if ((e = cudaMemsetAsync(n_out, 0, (size_t)B * sizeof(int), st)) != cudaSuccess) return e;
+  }
+  return cudaGetLastError();
+}
+
+size_t decode_smem_required(int H, int W, int K) { return detect_smem_bytes(H, W, K, K <= 1536 ? 4096 : 8192); }
+
+}  // namespace spvo

@@ -1,0 +1,152 @@
+"""GPU parity: CUDA decode (through the C ABI) vs the CPU oracle on identical seeded tensors.
+Bar: keypoint lists bit-exact including order; scores bit-exact; descriptors bit-exact (tolerance
+stated by north_star is 1e-5 abs; oracle and kernel share one arithmetic specification)."""
+import numpy as np
+import pytest
+
+from conftest import make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(fe, O, semi, desc, **cfg):
+    r = fe.decode(semi, desc, **cfg)
+    o = O.decode(semi, desc, **cfg)
+    assert (r["n"] == o["n"]).all(), (r["n"], o["n"])
+    for b in range(semi.shape[0]):
+        n = int(o["n"][b])
+        gk, ok = r["kpts"][b], o["kpts"][b]
+        same = gk[:n] == ok[:n]
+        if not same.all():
+            i = int(np.argmin(same))
+            raise AssertionError(f"image {b}: first keypoint mismatch at rank {i}: gpu {gk[i]} oracle {ok[i]} (n={n})")
+        assert (r["scores"][b, :n].view(np.uint32) == o["scores"][b, :n].view(np.uint32)).all()
+        if desc is not None:
+            d = np.abs(r["desc"][b, :n] - o["desc"][b, :n]).max() if n else 0.0
+            assert d <= 1e-5, f"descriptor max abs diff {d}"
+            assert (r["desc"][b, :n].view(np.uint32) == o["desc"][b, :n].view(np.uint32)).all(), "desc not bit-exact"
+        # rows beyond n are zero-filled
+        assert not r["kpts"][b, n:].view(np.uint8).any()
+    return r, o
+
+
+@pytest.mark.parametrize("H,W,K,sigma", [
+    (376, 1240, 1000, 1.0),   # config 1/2: KITTI-shaped
+    (376, 1240, 2048, 1.0),   # config 3
+    (192, 640, 500, 1.0),     # config 4
+    (360, 1176, 1000, 0.1),   # repo-native size, heavy score ties
+    (240, 784, 1000, 3.0),
+    (120, 392, 1000, 1.0),    # reference default ctor size: fewer survivors than K
+])
+def test_decode_parity(spvo, oracle, H, W, K, sigma):
+    fe = spvo.Frontend(0, 2, H, W, K)
+    semi, desc = make_inputs(2, H, W, seed=H + K, sigma=sigma)
+    _compare(fe, oracle, semi, desc, max_keypoints=K)
+    fe.close()
+
+
+def test_decode_exhaustive_walk_uses_slow_path(spvo, oracle):
+    """K larger than the number of NMS survivors: every candidate is walked (chunked exact path)."""
+    H, W, K = 192, 640, 4096
+    fe = spvo.Frontend(0, 1, H, W, K)
+    semi, desc = make_inputs(1, H, W, seed=5)
+    r, o = _compare(fe, oracle, semi, desc, max_keypoints=K)
+    assert o["n"][0] < K and o["walked"][0] == o["ncand"][0]
+    assert fe.debug_counters()[0] >= 1
+    fe.close()
+
+
+def test_decode_constant_logits_all_ties(spvo, oracle):
+    """All-equal logits: every pixel has the same score 1/65 > 0.015 -> pure tie-break order."""
+    H, W, K = 64, 96, 300
+    fe = spvo.Frontend(0, 1, H, W, K)
+    semi = np.zeros((1, 65, H // 8, W // 8), np.float32)
+    _, desc = make_inputs(1, H, W, seed=1)
+    _compare(fe, oracle, semi, desc, max_keypoints=K)
+    fe.close()
+
+
+@pytest.mark.parametrize("conf,dist,border", [(0.015, 4, 4), (0.05, 2, 0), (0.001, 8, 12), (0.3, 0, 1), (0.015, 16, 4)])
+def test_decode_parameter_sweep(spvo, oracle, conf, dist, border):
+    H, W, K = 128, 256, 700
+    fe = spvo.Frontend(0, 3, H, W, K)
+    semi, desc = make_inputs(3, H, W, seed=int(conf * 1000) + dist)
+    _compare(fe, oracle, semi, desc, conf_thresh=conf, dist_thresh=dist, border_remove=border, max_keypoints=K)
+    fe.close()
+
+
+def test_decode_no_candidates_and_k0(spvo, oracle):
+    H, W = 64, 64
+    fe = spvo.Frontend(0, 1, H, W, 100)
+    semi = np.zeros((1, 65, 8, 8), np.float32)
+    semi[:, 64] = 20.0  # all mass in the dustbin: nothing above threshold
+    _, desc = make_inputs(1, H, W)
+    r = fe.decode(semi, desc, max_keypoints=100)
+    assert r["n"][0] == 0 and not r["kpts"].view(np.uint8).any() and not r["desc"].any()
+    r = fe.decode(semi * 0, desc, max_keypoints=0)
+    assert r["n"][0] == 0
+    fe.close()
+
+
+def test_decode_known_answers(spvo, oracle):
+    """Hand-computable cases from SURVEY.md section 8c."""
+    H, W = 64, 96
+    fe = spvo.Frontend(0, 1, H, W, 50)
+    Hc, Wc = H // 8, W // 8
+    _, desc = make_inputs(1, H, W)
+
+    def one_hot(points, amp=12.0):
+        semi = np.zeros((1, 65, Hc, Wc), np.float32)
+        semi[:, 64] = 8.0
+        for k, (x, y) in enumerate(points):
+            semi[0, (y % 8) * 8 + (x % 8), y // 8, x // 8] = amp - 0.5 * k
+        return semi
+
+    # single peak -> single keypoint at (x, y)
+    r = fe.decode(one_hot([(41, 27)]), desc, max_keypoints=50)
+    assert r["n"][0] == 1 and (r["kpts"][0, 0]["x"], r["kpts"][0, 0]["y"]) == (41.0, 27.0)
+    assert r["kpts"][0, 0]["size"] == 1.0 and r["kpts"][0, 0]["angle"] == -1.0 and r["kpts"][0, 0]["class_id"] == -1
+    # two peaks at Chebyshev distance 4 (suppressed) vs 5 (both kept)
+    r = fe.decode(one_hot([(40, 30), (44, 30)]), desc, max_keypoints=50)
+    assert r["n"][0] == 1
+    r = fe.decode(one_hot([(40, 30), (45, 30)]), desc, max_keypoints=50)
+    assert r["n"][0] == 2 and r["kpts"][0, 0]["x"] == 40.0 and r["kpts"][0, 1]["x"] == 45.0
+    # a border peak suppresses its neighbour but is not emitted
+    r = fe.decode(one_hot([(2, 30), (5, 30)]), desc, max_keypoints=50)
+    assert r["n"][0] == 0
+    # K cut keeps the highest scores
+    pts = [(10 + 8 * i, 20) for i in range(8)]
+    r = fe.decode(one_hot(pts), desc, max_keypoints=3)
+    assert r["n"][0] == 3 and [int(v) for v in r["kpts"][0]["x"]] == [10, 18, 26]
+    fe.close()
+
+
+def test_decode_invalid_arguments(spvo):
+    fe = spvo.Frontend(0, 1, 64, 64, 10)
+    semi = np.zeros((1, 65, 8, 8), np.float32)
+    with pytest.raises(spvo.SpvoError):
+        fe.decode(semi, None, max_keypoints=11)          # above handle capacity
+    with pytest.raises(spvo.SpvoError):
+        fe.decode(np.zeros((2, 65, 8, 8), np.float32), None, max_keypoints=5)  # batch above capacity
+    with pytest.raises(spvo.SpvoError):
+        spvo.Frontend(0, 1, 60, 64, 10)                  # H % 8 != 0 (hpp:296)
+    fe.close()
+
+
+def test_decode_device_pointer_api_matches_host_api(spvo):
+    import torch
+    H, W, K, B = 192, 640, 500, 4
+    fe = spvo.Frontend(0, B, H, W, K)
+    semi, desc = make_inputs(B, H, W, seed=9)
+    r = fe.decode(semi, desc, max_keypoints=K)
+    ds, dd = torch.from_numpy(semi).cuda(), torch.from_numpy(desc).cuda()
+    kp = torch.zeros(B, K, 7, dtype=torch.float32, device="cuda")
+    do = torch.zeros(B, K, 256, device="cuda")
+    n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    fe.set_stream(torch.cuda.current_stream().cuda_stream)
+    fe.decode_device(ds, dd, B, H, W, kp, do, n, None, max_keypoints=K)
+    torch.cuda.synchronize()
+    assert (n.cpu().numpy() == r["n"]).all()
+    assert (kp.cpu().numpy().view(np.uint8).reshape(B, K, 28) == r["kpts"].view(np.uint8).reshape(B, K, 28)).all()
+    assert (do.cpu().numpy() == r["desc"]).all()
+    fe.close()

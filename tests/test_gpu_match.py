@@ -1,0 +1,108 @@
+"""GPU parity: CUDA matcher (through the C ABI) vs the CPU oracle (itself pinned to cv2.BFMatcher).
+Bar: (queryIdx, trainIdx) pairs, order, and the fp32 distance bits all exact."""
+import numpy as np
+import pytest
+
+from conftest import unit_rows
+
+pytestmark = pytest.mark.gpu
+
+MODES = [0, 1, 2]
+
+
+def _noisy_copy(a, seed, noise=0.05, perm=True):
+    rng = np.random.default_rng(seed)
+    b = a + noise * rng.standard_normal(a.shape).astype(np.float32)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    if perm:
+        b = b[rng.permutation(len(b))]
+    return b.astype(np.float32)
+
+
+def _check(fe, O, q, t, mode, algorithm=0):
+    gm, gmap = fe.match(q, t, mode=mode, ratio=0.8, algorithm=algorithm)
+    om, omap = O.match(q, t, mode=mode, ratio=0.8)
+    assert len(gm) == len(om), (len(gm), len(om))
+    assert (gm["queryIdx"] == om["queryIdx"]).all() and (gm["trainIdx"] == om["trainIdx"]).all()
+    assert (gm["imgIdx"] == 0).all()
+    assert (gm["distance"].view(np.uint32) == om["distance"].view(np.uint32)).all()
+    assert (gmap == omap).all()
+    return gm
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("N,M", [(1000, 1000), (777, 1023), (33, 2048), (1, 1), (2, 1), (500, 3)])
+def test_match_parity_structured(spvo, oracle, mode, N, M):
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    base = unit_rows(max(N, M), seed=N * 7 + M)
+    q = base[:N]
+    t = _noisy_copy(base, seed=3)[:M]
+    gm = _check(fe, oracle, q, t, mode)
+    if mode == 2 and N >= 500 and M >= 500:
+        assert len(gm) > 100  # ratio test is non-degenerate on structured data
+    fe.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_match_parity_random(spvo, oracle, mode):
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    _check(fe, oracle, unit_rows(600, 1), unit_rows(640, 2), mode)
+    fe.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_match_ties_lowest_index_wins(spvo, oracle, mode):
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    q, t = unit_rows(200, 11), unit_rows(220, 12)
+    t[50] = t[7]; t[120] = t[7]; t[121] = t[7]     # duplicate train rows
+    q[30] = q[4]; q[31] = q[4]                     # duplicate query rows
+    t[7] = q[4]                                    # an exact zero distance, shared
+    _check(fe, oracle, q, t, mode)
+    fe.close()
+
+
+def test_match_empty_inputs(spvo):
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    for mode in MODES:
+        m, q2t = fe.match(np.zeros((0, 256), np.float32), unit_rows(5), mode=mode)
+        assert len(m) == 0 and len(q2t) == 0
+        m, q2t = fe.match(unit_rows(5), np.zeros((0, 256), np.float32), mode=mode)
+        assert len(m) == 0 and (q2t == -1).all()
+    m, q2t = fe.match(unit_rows(5), unit_rows(1), mode=2)   # kNN with one train row: defined as no match
+    assert len(m) == 0 and (q2t == -1).all()
+    fe.close()
+
+
+def test_match_batch_device(spvo, oracle):
+    """Batched device API: slots as written by decode, per-slot row counts read on the device."""
+    import torch
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    S, stride = 6, 300
+    rows = [300, 250, 0, 1, 299, 128]
+    descs = np.zeros((S, stride, 256), np.float32)
+    base = unit_rows(stride, 5)
+    for s in range(S):
+        descs[s, : rows[s]] = _noisy_copy(base, seed=s, perm=(s % 2 == 1))[: rows[s]]
+    d = torch.from_numpy(descs).cuda()
+    n_rows = torch.tensor(rows, dtype=torch.int32, device="cuda")
+    qs = torch.tensor([0, 0, 1, 2, 3, 4, 5], dtype=torch.int32, device="cuda")
+    ts = torch.tensor([1, 4, 0, 1, 0, 5, 2], dtype=torch.int32, device="cuda")
+    P = len(qs)
+    fe.set_stream(torch.cuda.current_stream().cuda_stream)
+    for mode in MODES:
+        out = torch.zeros(P, stride, 4, dtype=torch.int32, device="cuda")
+        nm = torch.zeros(P, dtype=torch.int32, device="cuda")
+        q2t = torch.zeros(P, stride, dtype=torch.int32, device="cuda")
+        fe.match_batch_device(d, n_rows, stride, qs, ts, P, stride, out, nm, q2t, mode=mode)
+        torch.cuda.synchronize()
+        out_h = out.cpu().numpy().view(spvo.DMATCH_DTYPE).reshape(P, stride)
+        for p in range(P):
+            a, b = int(qs[p]), int(ts[p])
+            om, omap = oracle.match(descs[a, : rows[a]], descs[b, : rows[b]], mode=mode)
+            k = int(nm[p])
+            assert k == len(om)
+            g = out_h[p, :k]
+            assert (g["queryIdx"] == om["queryIdx"]).all() and (g["trainIdx"] == om["trainIdx"]).all()
+            assert (g["distance"].view(np.uint32) == om["distance"].view(np.uint32)).all()
+            assert (q2t[p, : rows[a]].cpu().numpy() == omap).all()
+    fe.close()
