@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frame-pairs/s of the SuperPoint decode + match front end on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of F synthetic stereo frame pairs
+(BASELINE.json configs[1]: KITTI-shaped 1240x376 stream, 1000 keypoints/image, NN + cross-check,
+left<->right and t<->t-1 matching, stereo row-band filter): 2F decodes + 2F matches + F filters,
+through ONE C-ABI call (spvo_stereo_batch_device / spvo_stereo_batch).
+
+  value     whole-job pairs/s with the batch's input tensors already resident in HBM (ring of
+            batches larger than L2), timed with CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the host-buffer C-ABI call (spvo_stereo_batch): pinned host
+            inputs -> H2D -> kernels -> D2H of keypoints / matches / maps, every step
+  roofline  dominant kernel of the step, timed live with CUDA events inside the timed region
+            (spvo_profile_*), against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference decode + cv::BFMatcher arithmetic) timed on this
+            host's cores on a bounded sample (rank 0, N = 1 only)
+
+Multi-GPU: frames are independent in the front end; rank r processes its own
+contiguous frame range with no data-path collective (weak scaling: per-GPU work fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, K = 376, 1240, 1000          # "1241x376" is not a multiple of 8; KITTI-shaped = 1240x376
+SEQ_LEN = 4541                     # KITTI seq 00 length
+WORKLOAD = "kitti_seq00_synth_1240x376_K1000_nn_crosscheck_stereo+temporal"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        self.lines = []
+        if self.proc:
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline and --impl reference).  The ONLY places bench.py executes oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_pairs_per_second(num_pairs: int, cores: int, ring_pairs: int = 8):
+    """Process `num_pairs` stereo pairs (2 decodes + stereo match + temporal match + row-band filter each)
+    with the CPU oracle, frames spread over `cores` threads (ctypes releases the GIL).  Returns
+    (pairs/s, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    import spvo_b200.synth as synth
+    O.build()
+    semi, desc = synth.make_stream(ring_pairs, H, W, seed=0, device="cpu")
+    semi, desc = semi.numpy(), desc.numpy()
+    decoded = [None] * num_pairs
+
+    def dec(i):
+        decoded[i] = O.decode(semi[i % ring_pairs], desc[i % ring_pairs], max_keypoints=K, num_threads=1)
+
+    def mat(i):
+        d = decoded[i]
+        nl, nr = int(d["n"][0]), int(d["n"][1])
+        m, _ = O.match(d["desc"][0, :nl], d["desc"][1, :nr], mode=O.MODE_NN_CROSSCHECK, num_threads=1)
+        O.stereo_filter(d["kpts"][0], d["kpts"][1], m)
+        if i > 0:
+            p = decoded[i - 1]
+            O.match(d["desc"][0, :nl], p["desc"][0, : int(p["n"][0])], mode=O.MODE_NN_CROSSCHECK, num_threads=1)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(dec, range(num_pairs)))
+        list(ex.map(mat, range(num_pairs)))
+    dt = time.perf_counter() - t0
+    return num_pairs / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port: the reference itself cannot be compiled
+    here) on this host's cores, same metric / config.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = host_cores()
+    # size one step so that the whole run stays within ~2 minutes
+    rate0, _ = cpu_pairs_per_second(max(2, min(cores, 16)), cores)
+    budget = 90.0 / max(1, args.steps + args.warmup)
+    step_pairs = int(max(2, min(SEQ_LEN, rate0 * budget)))
+    for _ in range(args.warmup):
+        cpu_pairs_per_second(step_pairs, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_pairs_per_second(step_pairs, cores)
+        t += dt
+    val = args.steps * step_pairs / t
+    sample = f"{step_pairs} pairs/step x {args.steps} steps, {cores} threads over frames, oracle port (C++), 1 thread per frame"
+    print(json.dumps({
+        "impl": "reference", "metric": "stereo_frame_pairs_per_sec_decode_match", "value": val, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": step_pairs, "H": H, "W": W, "keypoints": K,
+                   "match": "nn_crosscheck"},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import spvo_b200 as S
+    import spvo_b200.synth as synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = args.pairs_per_step
+    R = args.ring
+    peaks = load_peaks()
+
+    # rank r owns the contiguous frame range [r*shard, (r+1)*shard) of the sequence
+    shard = (SEQ_LEN + world - 1) // world
+    first = rank * shard
+    semi, desc = synth.make_stream(R * F, H, W, seed=0, device=dev, first_frame=first)
+    semi = semi.view(R, F, 2, 65, H // 8, W // 8)
+    desc = desc.view(R, F, 2, 256, H // 8, W // 8)
+    in_bytes = (semi[0].numel() + desc[0].numel()) * 4
+
+    fe = S.Frontend(local_rank, 2 * F, H, W, K)
+    # a dedicated non-default stream: the library enqueues on it and the timing events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    fe.set_stream(stream.cuda_stream)
+    out = fe.alloc_stereo_out(F, K, device=dev)
+    cfg = dict(max_keypoints=K, mode=S.MATCH_NN_CROSSCHECK, algorithm=args.algorithm, stereo_threshold=2.0,
+               min_disparity=0.25)
+
+    def step(i):
+        r = i % R
+        fe.stereo_batch_device(semi[r], desc[r], F, H, W, out, **cfg)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    fe.stereo_reset()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    fe.profile_enable(True)
+    fe.profile_read()
+    l0 = fe.kernel_launches
+    clocks = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    prof = fe.profile_read()
+    launches = fe.kernel_launches - l0
+    fe.profile_enable(False)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * F / (ms_max * 1e-3)
+    n_kp = out["n_kpts"].float().mean().item()
+    n_m = out["n_matches"].float().mean().item()
+
+    # ---------------- end to end through the host-buffer C-ABI call ----------------
+    Rh = 2
+    h_semi = torch.empty((Rh, F, 2, 65, H // 8, W // 8), dtype=torch.float32, pin_memory=True)
+    h_desc = torch.empty((Rh, F, 2, 256, H // 8, W // 8), dtype=torch.float32, pin_memory=True)
+    for r in range(Rh):
+        h_semi[r].copy_(semi[r])
+        h_desc[r].copy_(desc[r])
+    h_out = fe.alloc_stereo_out(F, K, device="cpu", pinned=True, with_desc=False)
+    d2h_bytes = sum(v.numel() * v.element_size() for v in h_out.values())
+    fe.stereo_reset()
+    for i in range(max(1, min(args.warmup, 3))):
+        fe.stereo_batch(h_semi[i % Rh], h_desc[i % Rh], F, H, W, h_out, **cfg)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        fe.stereo_batch(h_semi[i % Rh], h_desc[i % Rh], F, H, W, h_out, **cfg)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps * F / float(t.item())
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel ----------------
+        cells = (H // 8) * (W // 8)
+        B = 2 * F
+        alg = {  # algorithmic bytes (HBM-bound kernels) or flops (matching) per launch; DESIGN.md
+            "k_softmax_heat": ("hbm", B * 4 * 65 * cells),
+            "k_detect": ("hbm", B * K * 28),
+            "k_sample_desc": ("hbm", B * (4 * 256 * cells + K * 1024)),
+            "k_dist_exact": ("tensor", 2 * F * 2.0 * n_kp * n_kp * 256),
+            "k_tc_gemm": ("tensor", 2 * F * 2.0 * n_kp * n_kp * 256),
+        }
+        kernels = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / sum(x[0] for x in prof.values())}
+                   for k, v in prof.items()}
+        dom = max(prof, key=lambda k: prof[k][0])
+        bound, work = alg.get(dom, ("hbm", 0))
+        dur = prof[dom][0] / prof[dom][1] * 1e-3
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(f"{dom}@F{F}")
+        if bound == "hbm":
+            ach, peak, unit = work / dur / 1e9, peaks["hbm"], "GB/s"
+        else:
+            ach, peak, unit = work / dur / 1e12, peaks["tf_sus"], "TFLOP/s"
+        roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peaks["src"] + (" (sustained)" if bound == "tensor" else "")}
+        dec_ms = sum(prof[k][0] for k in ("k_softmax_heat", "k_detect", "k_sample_desc") if k in prof) / args.steps
+        dec_bytes = B * (4 * (65 + 256) * cells + K * 1052)
+        decode_roofline = {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                           "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peaks["hbm"],
+                           "note": "all decode kernels of a step vs SURVEY 8d bytes: 4*(65+256)*cells + K*1052 per image"}
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            r0, _ = cpu_pairs_per_second(max(2, min(cores, 16)), cores)
+            n_s = int(max(4, min(2048, r0 * 15.0)))
+            val, dt = cpu_pairs_per_second(n_s, cores)
+            cpu_baseline = {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                            "sample": f"{n_s} pairs of the same workload in {dt:.1f} s, {cores} threads over frames"}
+        print(json.dumps({
+            "metric": "stereo_frame_pairs_per_sec_decode_match", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": F, "H": H, "W": W, "keypoints": K,
+                       "match": "nn_crosscheck", "matcher_algorithm": args.algorithm,
+                       "l2": f"inputs cycle through a ring of {R} batches x {in_bytes / 1e6:.0f} MB (> 126 MB L2)",
+                       "frame_sharding": f"{world} contiguous ranges of {shard} frames",
+                       "mean_keypoints": n_kp, "mean_matches": n_m},
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": roofline,
+            "decode_roofline": decode_roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu_baseline,
+        }))
+    fe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-step", type=int, default=74, help="stereo pairs per batch (2F = 148 images = one CTA per SM in k_detect)")
+    ap.add_argument("--ring", type=int, default=3, help="distinct input batches cycled through (ring >> L2)")
+    ap.add_argument("--algorithm", type=int, default=0, help="SPVO_MATCHER_* (0 auto, 1 exact fp32, 2 tensor)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,11 +150,50 @@ int spvo_match_batch_device(spvo_handle h, const float* desc_base, const int* n_
 
 /* ---- stereo row-band / min-disparity test applied to L<->R matches (BASE:169-172):
  * keep[m] = !(|y_l - y_r| > stereo_threshold || |x_l - x_r| < min_disparity).
- * Device form, batched like spvo_match_batch_device (kpts_base slots of slot_stride_rows rows). */
+ * Device form, batched like spvo_match_batch_device (kpts_base slots of slot_stride_rows rows);
+ * q_slot / t_slot may both be NULL, meaning problem p uses slots (2p, 2p+1). */
 int spvo_stereo_filter_batch_device(spvo_handle h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                     const int* q_slot, const int* t_slot, int P, int max_rows,
                                     const spvo_dmatch* matches, const int* n_matches,
                                     float stereo_threshold, float min_disparity, uint8_t* keep);
+
+/* ---- stereo stream: one call per batch of F consecutive stereo frames.  Replaces, for every frame f,
+ * the front-end part of stereoCallback (visual_odometry_node.cpp:175-199):
+ *   addStereoImagePair -> postprocessDetectionAndDescription on (left_f, right_f)      (NN:468-484)
+ *   matchDescriptors(CURR_LEFT_CURR_RIGHT)   query = left_f, train = right_f           (HPP:88)
+ *   matchDescriptors(CURR_LEFT_PREV_LEFT)    query = left_f, train = left_{f-1}        (HPP:89)
+ *   the stereo row-band / min-disparity test of solveStereoOdometry on the L<->R matches (BASE:169-172)
+ * Frames are independent in the front end except for the one-frame dependency of the temporal
+ * match; the handle keeps the previous batch's last left image (descriptors, keypoints, count) on
+ * the device, so consecutive calls continue one sequence.  spvo_stereo_reset() forgets it
+ * (clearLagecyData, BASE:35-66): the next frame then has no temporal matches, as the reference's
+ * first frame (visual_odometry_node.cpp:188-193).
+ *   semi [F,2,65,H/8,W/8], desc [F,2,256,H/8,W/8]: image index 2f + eye, eye 0 = left (the batch-2
+ *   layout of NN:480-484).  2F <= max_batch of the handle.  K = cfg->decode.max_keypoints. */
+typedef struct spvo_stereo_cfg {
+  spvo_decode_cfg decode;
+  spvo_match_cfg match;
+  float stereo_threshold; /* stereo_threshold_, launch default 2.0  */
+  float min_disparity;    /* min_disparity_,   launch default 0.25 */
+} spvo_stereo_cfg;
+
+typedef struct spvo_stereo_out { /* all device pointers (_device form) or all host pointers */
+  spvo_keypoint* kpts;   /* [2F, K]                                                              */
+  float* desc;           /* [2F, K, 256]; host form: may be NULL (descriptors stay on the device) */
+  int* n_kpts;           /* [2F]                                                                  */
+  spvo_dmatch* matches;  /* [2F, K]: rows 0..F-1 stereo L_f->R_f, rows F..2F-1 temporal L_f->L_{f-1} */
+  int* n_matches;        /* [2F]                                                                  */
+  int* q2t;              /* [2F, K] maps_of_indices (HPP:161), -1 = unmatched                     */
+  uint8_t* stereo_keep;  /* [F, K]  1 = L<->R match m passes BASE:169-172                         */
+} spvo_stereo_out;
+
+int spvo_stereo_reset(spvo_handle h);
+int spvo_stereo_batch_device(spvo_handle h, const float* semi, const float* desc, int F, int H, int W,
+                             const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
+/* Host-pointer form: H2D of the inputs, the device pipeline, D2H of every non-NULL output, sync.
+ * Pinned host memory gives full PCIe rate. */
+int spvo_stereo_batch(spvo_handle h, const float* semi, const float* desc, int F, int H, int W,
+                      const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
 
 /* ---- introspection for tests / bench ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
@@ -163,6 +202,16 @@ long long spvo_kernel_launches(spvo_handle h);
  * decode: [0] images that left the histogram fast path (slow exact path taken), match: [1] rows
  * re-ranked by the exact full-row fallback, [2] candidate pairs re-ranked exactly. */
 int spvo_debug_counters(spvo_handle h, long long* out, int n);
+
+/* Optional per-kernel profile: when enabled every kernel launch is bracketed by CUDA events on
+ * the handle's stream (how bench.py measures the dominant kernel's duration live, inside its timed
+ * region).  spvo_profile_read synchronises the stream, returns the accumulated milliseconds and
+ * launch counts per kernel class since the last read and clears them.  Kernel classes are indexed
+ * 0 .. spvo_profile_num_kernels()-1; spvo_profile_kernel_name gives the kernel's name. */
+int spvo_profile_enable(spvo_handle h, int on);
+int spvo_profile_num_kernels(void);
+const char* spvo_profile_kernel_name(int kernel_class);
+int spvo_profile_read(spvo_handle h, double* ms, long long* launches, int n);
 
 #ifdef __cplusplus
 }

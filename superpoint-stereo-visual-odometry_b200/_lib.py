@@ -30,11 +30,23 @@ class MatchCfg(C.Structure):
     _fields_ = [("mode", C.c_int32), ("ratio", C.c_float), ("algorithm", C.c_int32), ("reserved", C.c_int32)]
 
 
+class StereoCfg(C.Structure):
+    _fields_ = [("decode", DecodeCfg), ("match", MatchCfg), ("stereo_threshold", C.c_float),
+                ("min_disparity", C.c_float)]
+
+
+class StereoOut(C.Structure):
+    _fields_ = [("kpts", C.c_void_p), ("desc", C.c_void_p), ("n_kpts", C.c_void_p), ("matches", C.c_void_p),
+                ("n_matches", C.c_void_p), ("q2t", C.c_void_p), ("stereo_keep", C.c_void_p)]
+
+
 # every symbol include/spvo_frontend.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
     "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
     "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
-    "spvo_stereo_filter_batch_device", "spvo_kernel_launches", "spvo_debug_counters",
+    "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch",
+    "spvo_kernel_launches", "spvo_debug_counters", "spvo_profile_enable", "spvo_profile_num_kernels",
+    "spvo_profile_kernel_name", "spvo_profile_read",
 ]
 
 _lib = None
@@ -65,12 +77,23 @@ def load():
     L.spvo_match_device.argtypes = mat
     L.spvo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
     L.spvo_stereo_filter_batch_device.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp, vp, cf, cf, vp]
+    L.spvo_stereo_reset.argtypes = [vp]
+    ster = [vp, vp, vp, ci, ci, ci, C.POINTER(StereoCfg), C.POINTER(StereoOut)]
+    L.spvo_stereo_batch_device.argtypes = ster
+    L.spvo_stereo_batch.argtypes = ster
     L.spvo_kernel_launches.restype = C.c_longlong
     L.spvo_kernel_launches.argtypes = [vp]
     L.spvo_debug_counters.argtypes = [vp, vp, ci]
+    L.spvo_profile_enable.argtypes = [vp, ci]
+    L.spvo_profile_enable.restype = ci
+    L.spvo_profile_num_kernels.restype = ci
+    L.spvo_profile_kernel_name.restype = C.c_char_p
+    L.spvo_profile_kernel_name.argtypes = [ci]
+    L.spvo_profile_read.argtypes = [vp, vp, vp, ci]
+    L.spvo_profile_read.restype = ci
     for name in ("spvo_create", "spvo_destroy", "spvo_set_stream", "spvo_sync", "spvo_decode", "spvo_decode_device",
                  "spvo_match", "spvo_match_device", "spvo_match_batch_device", "spvo_stereo_filter_batch_device",
-                 "spvo_debug_counters"):
+                 "spvo_debug_counters", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch"):
         getattr(L, name).restype = ci
     _lib = L
     return L

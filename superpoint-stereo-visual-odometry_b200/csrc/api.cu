@@ -123,9 +123,15 @@ int spvo_destroy(spvo_handle hh) {
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   void* ptrs[] = {h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
-                  h->st_matches, h->st_q2t, h->st_nm};
+                  h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n,
+                  h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (const ProfRec& r : h->prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SPVO_OK;
@@ -309,9 +315,158 @@ int spvo_stereo_filter_batch_device(spvo_handle hh, const spvo_keypoint* kpts_ba
   return SPVO_OK;
 }
 
+int spvo_stereo_reset(spvo_handle hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  DeviceGuard g(h->device);
+  h->has_prev = false;
+  if (h->carry_n) CK(cudaMemsetAsync(h->carry_n, 0, sizeof(int), h->stream));
+  return SPVO_OK;
+}
+
+static int check_stereo_args(Handle* h, const float* semi, const float* desc, int F, int H, int W,
+                             const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  if (!h) return SPVO_EINVAL;
+  if (!cfg || !out || !desc) return fail(h, SPVO_EINVAL, "stereo_batch: NULL argument");
+  if (F < 0 || 2 * F > h->max_batch) return fail(h, SPVO_EINVAL, "stereo_batch: 2*F = %d exceeds max_batch %d", 2 * F, h->max_batch);
+  if (!out->kpts || !out->n_kpts || !out->matches || !out->n_matches)
+    return fail(h, SPVO_EINVAL, "stereo_batch: kpts, n_kpts, matches and n_matches outputs are required");
+  int rc = check_decode_args(h, semi, 2 * F, H, W, &cfg->decode, out->kpts, out->n_kpts);
+  if (rc) return rc;
+  if (cfg->decode.max_keypoints < 1) return fail(h, SPVO_EINVAL, "stereo_batch: max_keypoints must be >= 1");
+  return check_match_cfg(h, &cfg->match, SPVO_DESC_DIM);
+}
+
+static int ensure_carry(Handle* h) {
+  if (h->carry_desc) return SPVO_OK;
+  const size_t K = h->max_k > 0 ? h->max_k : 1;
+  CK(cudaMalloc((void**)&h->carry_desc, K * 256 * sizeof(float)));
+  CK(cudaMalloc((void**)&h->carry_kpts, K * sizeof(spvo_keypoint)));
+  CK(cudaMalloc((void**)&h->carry_n, sizeof(int)));
+  CK(cudaMemsetAsync(h->carry_n, 0, sizeof(int), h->stream));
+  h->has_prev = false;
+  return SPVO_OK;
+}
+
+// The device pipeline shared by both forms.  desc_out must be a device buffer [2F,K,256].
+static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int F, int H, int W,
+                           const spvo_stereo_cfg* cfg, spvo_keypoint* kpts, float* desc_out, int* n_kpts,
+                           spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep) {
+  const int K = cfg->decode.max_keypoints;
+  cudaStream_t st = h->stream;
+  int rc = ensure_carry(h);
+  if (rc) return rc;
+  CK(launch_decode(h, semi, desc, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr));
+  if (2 * F > h->probs_cap) {
+    cudaFree(h->probs);
+    h->probs = nullptr;
+    h->probs_cap = 0;
+    CK(cudaMalloc((void**)&h->probs, (size_t)2 * F * sizeof(MatchProblem)));
+    h->probs_cap = 2 * F;
+  }
+  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K));
+  rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K);
+  if (rc) return rc;
+  if (keep)
+    CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
+                            cfg->min_disparity, keep));
+  // carry the last left image for the next batch's first temporal match
+  const size_t last = (size_t)2 * (F - 1);
+  CK(cudaMemcpyAsync(h->carry_desc, desc_out + last * K * 256, (size_t)K * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->carry_kpts, kpts + last * K, (size_t)K * sizeof(spvo_keypoint), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->carry_n, n_kpts + last, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  h->has_prev = true;
+  return SPVO_OK;
+}
+
+int spvo_stereo_batch_device(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
+                             const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_stereo_args(h, semi, desc, F, H, W, cfg, out);
+  if (rc) return rc;
+  if (!out->desc) return fail(h, SPVO_EINVAL, "stereo_batch_device: desc output is required");
+  if (F == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  return stereo_pipeline(h, semi, desc, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
+                         out->n_matches, out->q2t, out->stereo_keep);
+}
+
+int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
+                      const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_stereo_args(h, semi, desc, F, H, W, cfg, out);
+  if (rc) return rc;
+  if (F == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const size_t cells = (size_t)(H / 8) * (W / 8), K = cfg->decode.max_keypoints, B = (size_t)2 * F;
+  if (!h->st_smatches) {
+    const size_t mb = h->max_batch, mk = h->max_k > 0 ? h->max_k : 1;
+    CK(cudaMalloc((void**)&h->st_smatches, mb * mk * sizeof(spvo_dmatch)));
+    CK(cudaMalloc((void**)&h->st_snm, mb * sizeof(int)));
+    CK(cudaMalloc((void**)&h->st_sq2t, mb * mk * sizeof(int)));
+    CK(cudaMalloc((void**)&h->st_skeep, mb * mk));
+  }
+  CK(cudaMemcpyAsync(h->st_semi, semi, B * 65 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->st_desc, desc, B * 256 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = stereo_pipeline(h, h->st_semi, h->st_desc, F, H, W, cfg, h->st_kpts, h->st_desc_out, h->st_n, h->st_smatches,
+                       h->st_snm, h->st_sq2t, out->stereo_keep ? h->st_skeep : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out->kpts, h->st_kpts, B * K * sizeof(spvo_keypoint), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out->n_kpts, h->st_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (out->desc) CK(cudaMemcpyAsync(out->desc, h->st_desc_out, B * K * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out->matches, h->st_smatches, B * K * sizeof(spvo_dmatch), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out->n_matches, h->st_snm, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (out->q2t) CK(cudaMemcpyAsync(out->q2t, h->st_sq2t, B * K * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (out->stereo_keep) CK(cudaMemcpyAsync(out->stereo_keep, h->st_skeep, (size_t)F * K, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SPVO_OK;
+}
+
 long long spvo_kernel_launches(spvo_handle hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   return h ? h->launches : -1;
+}
+
+static const char* kKernelNames[KID_COUNT] = {
+    "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
+    "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank"};
+
+int spvo_profile_num_kernels(void) { return KID_COUNT; }
+
+const char* spvo_profile_kernel_name(int k) { return (k >= 0 && k < KID_COUNT) ? kKernelNames[k] : ""; }
+
+int spvo_profile_enable(spvo_handle hh, int on) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  h->profiling = on != 0;
+  return SPVO_OK;
+}
+
+int spvo_profile_read(spvo_handle hh, double* ms, long long* launches, int n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || n < 0) return SPVO_EINVAL;
+  DeviceGuard g(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  for (const ProfRec& r : h->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      h->prof_ms[r.kid] += t;
+      h->prof_n[r.kid] += 1;
+    }
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  h->prof_recs.clear();
+  for (int i = 0; i < n && i < KID_COUNT; ++i) {
+    if (ms) ms[i] = h->prof_ms[i];
+    if (launches) launches[i] = h->prof_n[i];
+  }
+  for (int i = 0; i < KID_COUNT; ++i) {
+    h->prof_ms[i] = 0;
+    h->prof_n[i] = 0;
+  }
+  return SPVO_OK;
 }
 
 int spvo_debug_counters(spvo_handle hh, long long* out, int n) {

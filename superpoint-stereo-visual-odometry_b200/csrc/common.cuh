@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "spvo_frontend.h"
 
 namespace spvo {
@@ -17,6 +19,17 @@ constexpr int kHistShift = 14;
 constexpr uint32_t kOneBits = 0x3F800000u;
 
 struct Handle;
+
+// Kernel classes, for launch counting and the optional per-kernel CUDA-event profile
+// (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
+enum KernelId {
+  KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_COUNT
+};
+struct ProfRec {
+  int kid;
+  cudaEvent_t a, b;
+};
 
 // One matching problem, resident on the device (built by k_setup_problems / k_set_problem).
 struct MatchProblem {
@@ -35,6 +48,8 @@ cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int 
                                int out_stride);
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
+cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
+                                         int F, int K);
 cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
 cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                  const int* q_slot, const int* t_slot, int P, int max_rows,
@@ -73,8 +88,55 @@ struct Handle {
   int* st_q2t = nullptr;
   int* st_nm = nullptr;
   size_t st_rows = 0;
+  // stereo stream state: previous batch's last left image
+  float* carry_desc = nullptr;      // [max_k, 256]
+  spvo_keypoint* carry_kpts = nullptr;
+  int* carry_n = nullptr;           // device int; 0 when there is no previous frame
+  bool has_prev = false;
+  // host-form staging of the stereo outputs
+  spvo_dmatch* st_smatches = nullptr;
+  int* st_snm = nullptr;
+  int* st_sq2t = nullptr;
+  uint8_t* st_skeep = nullptr;
   long long launches = 0;
+  // optional per-kernel profile
+  bool profiling = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[KID_COUNT] = {0};
+  long long prof_n[KID_COUNT] = {0};
   char err[512] = {0};
+};
+
+// Counts the launch and, when profiling is on, brackets it with CUDA events on the handle's stream.
+struct LaunchScope {
+  Handle* h;
+  int kid;
+  cudaEvent_t a = nullptr;
+  static cudaEvent_t get(Handle* h) {
+    if (!h->ev_pool.empty()) {
+      cudaEvent_t e = h->ev_pool.back();
+      h->ev_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  LaunchScope(Handle* h_, int kid_) : h(h_), kid(kid_) {
+    h->launches++;
+    if (h->profiling) {
+      a = get(h);
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (a) {
+      cudaEvent_t b = get(h);
+      cudaEventRecord(b, h->stream);
+      h->prof_recs.push_back({kid, a, b});
+    }
+  }
 };
 
 __device__ __forceinline__ uint32_t fbits(float f) { return __float_as_uint(f); }

@@ -491,8 +491,10 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
   if (B == 0) return cudaSuccess;
   if ((e = cudaMemsetAsync(h->hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
   dim3 g1((cells + 31) / 32, B);
-  k_softmax_heat<<<g1, 256, 0, st>>>(semi, h->heat, h->hist, Hc, Wc, cfg.conf_thresh);
-  h->launches++;
+  {
+    LaunchScope ls(h, KID_SOFTMAX_HEAT);
+    k_softmax_heat<<<g1, 256, 0, st>>>(semi, h->heat, h->hist, Hc, Wc, cfg.conf_thresh);
+  }
   if (K > 0) {
     DetectParams p;
     p.heat = h->heat; p.hist = h->hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
@@ -503,12 +505,14 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
     const size_t smem = detect_smem_bytes(H, W, K, p.cap);
     if ((e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return e;
-    k_detect<<<B, kDetectThreads, smem, st>>>(p);
-    h->launches++;
+    {
+      LaunchScope ls(h, KID_DETECT);
+      k_detect<<<B, kDetectThreads, smem, st>>>(p);
+    }
     if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);
+      LaunchScope ls(h, KID_SAMPLE_DESC);
       k_sample_desc<<<g3, 256, 0, st>>>(desc, kpts, n_out, desc_out, H, W, K);
-      h->launches++;
     }
   } else {
     if ((e = cudaMemsetAsync(n_out, 0, (size_t)B * sizeof(int), st)) != cudaSuccess) return e;

@@ -231,6 +231,33 @@ __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, co
   probs[p] = pr;
 }
 
+// Stereo stream problems: p < F stereo (left_f vs right_f); p >= F temporal (left_f vs left_{f-1},
+// or the carried last-left of the previous batch for f = 0; carry_n = 0 means "no previous frame").
+__global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_out, const int* n_out,
+                                        const float* carry_desc, const int* carry_n, int F, int K) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 2 * F) return;
+  MatchProblem pr;
+  if (p < F) {
+    pr.q = desc_out + (size_t)(2 * p) * K * kD;
+    pr.t = desc_out + (size_t)(2 * p + 1) * K * kD;
+    pr.N = n_out[2 * p];
+    pr.M = n_out[2 * p + 1];
+  } else {
+    const int f = p - F;
+    pr.q = desc_out + (size_t)(2 * f) * K * kD;
+    pr.N = n_out[2 * f];
+    if (f > 0) {
+      pr.t = desc_out + (size_t)(2 * (f - 1)) * K * kD;
+      pr.M = n_out[2 * (f - 1)];
+    } else {
+      pr.t = carry_desc;
+      pr.M = *carry_n;
+    }
+  }
+  probs[p] = pr;
+}
+
 __global__ void k_set_problem(MatchProblem* probs, const float* q, int N, const float* t, int M) {
   MatchProblem pr;
   pr.q = q; pr.t = t; pr.N = N; pr.M = M;
@@ -248,8 +275,9 @@ __global__ void k_stereo_filter(const spvo_keypoint* __restrict__ kpts_base, int
   uint8_t k = 0;
   if (m < n_matches[p]) {
     const spvo_dmatch dm = matches[(size_t)p * max_rows + m];
-    const spvo_keypoint a = kpts_base[(size_t)q_slot[p] * slot_stride_rows + dm.queryIdx];
-    const spvo_keypoint c = kpts_base[(size_t)t_slot[p] * slot_stride_rows + dm.trainIdx];
+    const int qs = q_slot ? q_slot[p] : 2 * p, ts = t_slot ? t_slot[p] : 2 * p + 1;
+    const spvo_keypoint a = kpts_base[(size_t)qs * slot_stride_rows + dm.queryIdx];
+    const spvo_keypoint c = kpts_base[(size_t)ts * slot_stride_rows + dm.trainIdx];
     const bool drop = fabsf(__fsub_rn(a.y, c.y)) > stereo_threshold || fabsf(__fsub_rn(a.x, c.x)) < min_disparity;
     k = drop ? 0 : 1;
   }
@@ -288,35 +316,58 @@ cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int 
   if ((e = ensure((void**)&h->col_best, &h->sel_cols, (size_t)P * mc, sizeof(int))) != cudaSuccess) return e;
   if (max_rows > 0 && max_cols > 0) {
     dim3 g((max_cols + kTile - 1) / kTile, (max_rows + kTile - 1) / kTile, P);
-    k_dist_exact<<<g, 256, 0, st>>>(probs, h->dist, mr, mc);
-    h->launches++;
+    {
+      LaunchScope ls(h, KID_DIST_EXACT);
+      k_dist_exact<<<g, 256, 0, st>>>(probs, h->dist, mr, mc);
+    }
     dim3 gr((max_rows + 7) / 8, P);
-    k_row_select<<<gr, 256, 0, st>>>(probs, h->dist, mr, mc, h->row_best, h->row_d);
-    h->launches++;
+    {
+      LaunchScope ls(h, KID_ROW_SELECT);
+      k_row_select<<<gr, 256, 0, st>>>(probs, h->dist, mr, mc, h->row_best, h->row_d);
+    }
     if (cfg.mode == SPVO_MATCH_NN_CROSSCHECK) {
       dim3 gc((max_cols + 31) / 32, P);
-      k_col_select<<<gc, 256, 0, st>>>(probs, h->dist, mr, mc, h->col_best);
-      h->launches++;
+      {
+        LaunchScope ls(h, KID_COL_SELECT);
+        k_col_select<<<gc, 256, 0, st>>>(probs, h->dist, mr, mc, h->col_best);
+      }
     }
   }
-  k_finalize_matches<<<P, 1024, 0, st>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode, cfg.ratio,
-                                         out, n_matches, q2t, out_stride);
-  h->launches++;
+  {
+    LaunchScope ls(h, KID_FINALIZE);
+    k_finalize_matches<<<P, 1024, 0, st>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode, cfg.ratio,
+                                           out, n_matches, q2t, out_stride);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P) {
   if (P == 0) return cudaSuccess;
-  k_setup_problems<<<(P + 127) / 128, 128, 0, h->stream>>>(probs, desc_base, n_rows, slot_stride_rows, q_slot,
-                                                          t_slot, P);
-  h->launches++;
+  {
+    LaunchScope ls(h, KID_SETUP);
+    k_setup_problems<<<(P + 127) / 128, 128, 0, h->stream>>>(probs, desc_base, n_rows, slot_stride_rows, q_slot,
+                                                            t_slot, P);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
+                                         int F, int K) {
+  if (F == 0) return cudaSuccess;
+  {
+    LaunchScope ls(h, KID_SETUP);
+    k_setup_stereo_problems<<<(2 * F + 127) / 128, 128, 0, h->stream>>>(probs, desc_out, n_out, h->carry_desc,
+                                                                       h->carry_n, F, K);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M) {
-  k_set_problem<<<1, 1, 0, h->stream>>>(probs, q, N, t, M);
-  h->launches++;
+  {
+    LaunchScope ls(h, KID_SETUP);
+    k_set_problem<<<1, 1, 0, h->stream>>>(probs, q, N, t, M);
+  }
   return cudaGetLastError();
 }
 
@@ -326,9 +377,11 @@ cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int 
                                  float min_disparity, uint8_t* keep) {
   if (P == 0 || max_rows == 0) return cudaSuccess;
   dim3 g((max_rows + 255) / 256, P);
-  k_stereo_filter<<<g, 256, 0, h->stream>>>(kpts_base, slot_stride_rows, q_slot, t_slot, max_rows, matches,
-                                            n_matches, stereo_threshold, min_disparity, keep);
-  h->launches++;
+  {
+    LaunchScope ls(h, KID_STEREO_FILTER);
+    k_stereo_filter<<<g, 256, 0, h->stream>>>(kpts_base, slot_stride_rows, q_slot, t_slot, max_rows, matches,
+                                              n_matches, stereo_threshold, min_disparity, keep);
+  }
   return cudaGetLastError();
 }
 

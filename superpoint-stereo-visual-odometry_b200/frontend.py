@@ -82,6 +82,17 @@ class Frontend:
         self._check(self._L.spvo_debug_counters(self._h, out.ctypes.data, 8))
         return out
 
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.spvo_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last read (synchronises the stream)."""
+        n = self._L.spvo_profile_num_kernels()
+        ms, cnt = np.zeros(n, np.float64), np.zeros(n, np.int64)
+        self._check(self._L.spvo_profile_read(self._h, ms.ctypes.data, cnt.ctypes.data, n))
+        return {self._L.spvo_profile_kernel_name(i).decode(): (float(ms[i]), int(cnt[i]))
+                for i in range(n) if cnt[i] > 0}
+
     # ---- decode -------------------------------------------------------------------------------
     def decode(self, semi: np.ndarray, desc: Optional[np.ndarray], conf_thresh=0.015, dist_thresh=4,
                border_remove=4, max_keypoints=1000, want_scores=True):
@@ -143,6 +154,55 @@ class Frontend:
         self._check(self._L.spvo_stereo_filter_batch_device(self._h, _ptr(kpts_base), slot_stride_rows, _ptr(q_slot),
                                                             _ptr(t_slot), P, max_rows, _ptr(matches), _ptr(n_matches),
                                                             stereo_threshold, min_disparity, _ptr(keep)))
+
+
+    # ---- stereo stream ----------------------------------------------------------------------
+    def stereo_reset(self):
+        self._check(self._L.spvo_stereo_reset(self._h))
+
+    @staticmethod
+    def _stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
+                    stereo_threshold, min_disparity):
+        return _lib.StereoCfg(DecodeCfg(conf_thresh, dist_thresh, border_remove, int(max_keypoints)),
+                              MatchCfg(mode, ratio, algorithm, 0), stereo_threshold, min_disparity)
+
+    def stereo_batch_device(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
+                            max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
+                            stereo_threshold=2.0, min_disparity=0.25):
+        """spvo_stereo_batch_device.  `out` maps the spvo_stereo_out field names to CUDA tensors."""
+        cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
+                               stereo_threshold, min_disparity)
+        so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
+                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep")])
+        self._check(self._L.spvo_stereo_batch_device(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg),
+                                                     C.byref(so)))
+
+    def stereo_batch(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
+                     max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
+                     stereo_threshold=2.0, min_disparity=0.25):
+        """spvo_stereo_batch (host pointers: numpy arrays or pinned CPU torch tensors); synchronous."""
+        cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
+                               stereo_threshold, min_disparity)
+        so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
+                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep")])
+        self._check(self._L.spvo_stereo_batch(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg), C.byref(so)))
+
+    @staticmethod
+    def alloc_stereo_out(F, K, device="cuda", pinned=False, with_desc=True):
+        """Output buffers of spvo_stereo_out as torch tensors (device or pinned host)."""
+        import torch
+        kw = dict(device=device) if device != "cpu" else dict(pin_memory=pinned)
+        out = dict(
+            kpts=torch.zeros(2 * F, K, 7, dtype=torch.float32, **kw),
+            n_kpts=torch.zeros(2 * F, dtype=torch.int32, **kw),
+            matches=torch.zeros(2 * F, K, 4, dtype=torch.int32, **kw),
+            n_matches=torch.zeros(2 * F, dtype=torch.int32, **kw),
+            q2t=torch.zeros(2 * F, K, dtype=torch.int32, **kw),
+            stereo_keep=torch.zeros(F, K, dtype=torch.uint8, **kw),
+        )
+        if with_desc:
+            out["desc"] = torch.zeros(2 * F, K, 256, dtype=torch.float32, **kw)
+        return out
 
 
 class SuperPointFeatureFrontEnd:

@@ -1,0 +1,82 @@
+"""GPU parity of the batched stereo-stream entry points (spvo_stereo_batch[_device]) against the
+oracle run frame by frame the way the reference's stereoCallback does (visual_odometry_node.cpp:175-199)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_stream(O, semi, desc, K, mode, thr, mind):
+    """semi [F,2,65,Hc,Wc] -> per-frame oracle results."""
+    F = semi.shape[0]
+    res, prev = [], None
+    for f in range(F):
+        d = O.decode(semi[f], desc[f], max_keypoints=K)
+        nl, nr = int(d["n"][0]), int(d["n"][1])
+        ms, maps = O.match(d["desc"][0, :nl], d["desc"][1, :nr], mode=mode)
+        keep = O.stereo_filter(d["kpts"][0], d["kpts"][1], ms, thr, mind)
+        if prev is not None:
+            mt, mapt = O.match(d["desc"][0, :nl], prev["desc"][0, : int(prev["n"][0])], mode=mode)
+        else:
+            mt, mapt = np.zeros(0, O.DMATCH_DTYPE), np.full(nl, -1, np.int32)
+        res.append(dict(dec=d, ms=ms, maps=maps, keep=keep, mt=mt, mapt=mapt))
+        prev = d
+    return res
+
+
+def _check_batch(S, out, ref, f0, F, K):
+    kp = out["kpts"].view(S.KEYPOINT_DTYPE).reshape(2 * F, K)
+    mm = out["matches"].view(S.DMATCH_DTYPE).reshape(2 * F, K)
+    for f in range(F):
+        r = ref[f0 + f]
+        for eye in range(2):
+            n = int(r["dec"]["n"][eye])
+            assert out["n_kpts"][2 * f + eye] == n
+            assert (kp[2 * f + eye, :n] == r["dec"]["kpts"][eye, :n]).all()
+            if "desc" in out:
+                assert (out["desc"][2 * f + eye, :n] == r["dec"]["desc"][eye, :n]).all()
+        for row, m, mp in ((f, r["ms"], r["maps"]), (F + f, r["mt"], r["mapt"])):
+            k = int(out["n_matches"][row])
+            assert k == len(m), (row, k, len(m))
+            g = mm[row, :k]
+            assert (g["queryIdx"] == m["queryIdx"]).all() and (g["trainIdx"] == m["trainIdx"]).all()
+            assert (g["distance"].view(np.uint32) == m["distance"].view(np.uint32)).all()
+            assert (out["q2t"][row, : len(mp)] == mp).all()
+        assert (out["stereo_keep"][f, : len(r["keep"])].astype(bool) == r["keep"]).all()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_stereo_batch_host_and_device(spvo, oracle, mode):
+    import torch
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, F, NB = 192, 640, 500, 3, 2
+    semi, desc = synth.make_stream(F * NB, H, W, seed=3, device="cpu")
+    semi, desc = semi.numpy(), desc.numpy()
+    ref = _oracle_stream(oracle, semi, desc, K, mode, 2.0, 0.25)
+    assert sum(len(r["ms"]) for r in ref) > 100 and sum(len(r["mt"]) for r in ref) > 100
+    kw = dict(max_keypoints=K, mode=mode, stereo_threshold=2.0, min_disparity=0.25)
+
+    # host-pointer form, two consecutive batches (the second one's first temporal match uses the carry)
+    fe = S.Frontend(0, 2 * F, H, W, K)
+    for b in range(NB):
+        out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
+        fe.stereo_batch(semi[b * F:(b + 1) * F], desc[b * F:(b + 1) * F], F, H, W, out, **kw)
+        _check_batch(S, out, ref, b * F, F, K)
+    # reset forgets the previous frame: batch 1 alone has no temporal match for its first frame
+    fe.stereo_reset()
+    out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
+    fe.stereo_batch(semi[F:2 * F], desc[F:2 * F], F, H, W, out, **kw)
+    assert out["n_matches"][F] == 0 and out["n_matches"][F + 1] == len(ref[F + 1]["mt"])
+    fe.close()
+
+    # device-pointer form on the torch stream
+    fe = S.Frontend(0, 2 * F, H, W, K)
+    fe.set_stream(torch.cuda.current_stream().cuda_stream)
+    ds, dd = torch.from_numpy(semi).cuda(), torch.from_numpy(desc).cuda()
+    for b in range(NB):
+        dout = fe.alloc_stereo_out(F, K, device="cuda")
+        fe.stereo_batch_device(ds[b * F:(b + 1) * F], dd[b * F:(b + 1) * F], F, H, W, dout, **kw)
+        torch.cuda.synchronize()
+        _check_batch(S, {k: v.cpu().numpy() for k, v in dout.items()}, ref, b * F, F, K)
+    fe.close()
