@@ -121,6 +121,7 @@ int spvo_destroy(spvo_handle hh) {
   if (!h) return SPVO_OK;
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  tc_workspace_free(h);
   void* ptrs[] = {h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n,
@@ -220,8 +221,14 @@ static int check_match_cfg(Handle* h, const spvo_match_cfg* cfg, int dim) {
 
 static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride) {
-  // SPVO_MATCHER_TENSOR is dispatched here once the tcgen05 path lands; AUTO = exact for now.
-  CK(launch_match_exact(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
+  // AUTO: the tensor-core path unless the problems are too small to fill a 128 x 128 tile.
+  int alg = cfg->algorithm;
+  if (alg == SPVO_MATCHER_AUTO)
+    alg = ((long long)max_rows * max_cols >= 128 * 128) ? SPVO_MATCHER_TENSOR : SPVO_MATCHER_EXACT_FP32;
+  if (alg == SPVO_MATCHER_TENSOR)
+    CK(launch_match_tc(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
+  else
+    CK(launch_match_exact(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
   return SPVO_OK;
 }
 

@@ -46,6 +46,9 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
 cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                                const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
                                int out_stride);
+cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride);
+void tc_workspace_free(Handle* h);
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
@@ -98,6 +101,7 @@ struct Handle {
   int* st_snm = nullptr;
   int* st_sq2t = nullptr;
   uint8_t* st_skeep = nullptr;
+  void* tc_ws = nullptr;  // TcWorkspace (match_tc.cu)
   long long launches = 0;
   // optional per-kernel profile
   bool profiling = false;

@@ -297,14 +297,8 @@ static cudaError_t ensure(void** ptr, size_t* have, size_t want, size_t elem) {
   return e;
 }
 
-cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
-                               const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
-                               int out_stride) {
-  cudaStream_t st = h->stream;
+cudaError_t ensure_select_buffers(Handle* h, int P, int mr, int mc) {
   cudaError_t e;
-  if (P == 0) return cudaSuccess;
-  const int mr = max_rows > 0 ? max_rows : 1, mc = max_cols > 0 ? max_cols : 1;
-  if ((e = ensure((void**)&h->dist, &h->dist_elems, (size_t)P * mr * mc, sizeof(float))) != cudaSuccess) return e;
   if (h->sel_rows < (size_t)P * mr) {
     if (h->row_best) cudaFree(h->row_best);
     if (h->row_d) cudaFree(h->row_d);
@@ -313,7 +307,29 @@ cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int 
     if ((e = cudaMalloc(&h->row_d, (size_t)P * mr * 2 * sizeof(float))) != cudaSuccess) return e;
     h->sel_rows = (size_t)P * mr;
   }
-  if ((e = ensure((void**)&h->col_best, &h->sel_cols, (size_t)P * mc, sizeof(int))) != cudaSuccess) return e;
+  return ensure((void**)&h->col_best, &h->sel_cols, (size_t)P * mc, sizeof(int));
+}
+
+cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, int mr, int mc,
+                                 const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
+                                 int out_stride) {
+  {
+    LaunchScope ls(h, KID_FINALIZE);
+    k_finalize_matches<<<P, 1024, 0, h->stream>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode,
+                                                  cfg.ratio, out, n_matches, q2t, out_stride);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                               const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
+                               int out_stride) {
+  cudaStream_t st = h->stream;
+  cudaError_t e;
+  if (P == 0) return cudaSuccess;
+  const int mr = max_rows > 0 ? max_rows : 1, mc = max_cols > 0 ? max_cols : 1;
+  if ((e = ensure((void**)&h->dist, &h->dist_elems, (size_t)P * mr * mc, sizeof(float))) != cudaSuccess) return e;
+  if ((e = ensure_select_buffers(h, P, mr, mc)) != cudaSuccess) return e;
   if (max_rows > 0 && max_cols > 0) {
     dim3 g((max_cols + kTile - 1) / kTile, (max_rows + kTile - 1) / kTile, P);
     {
@@ -327,18 +343,11 @@ cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int 
     }
     if (cfg.mode == SPVO_MATCH_NN_CROSSCHECK) {
       dim3 gc((max_cols + 31) / 32, P);
-      {
-        LaunchScope ls(h, KID_COL_SELECT);
-        k_col_select<<<gc, 256, 0, st>>>(probs, h->dist, mr, mc, h->col_best);
-      }
+      LaunchScope ls(h, KID_COL_SELECT);
+      k_col_select<<<gc, 256, 0, st>>>(probs, h->dist, mr, mc, h->col_best);
     }
   }
-  {
-    LaunchScope ls(h, KID_FINALIZE);
-    k_finalize_matches<<<P, 1024, 0, st>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode, cfg.ratio,
-                                           out, n_matches, q2t, out_stride);
-  }
-  return cudaGetLastError();
+  return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
 }
 
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,

@@ -1,0 +1,552 @@
+// match_tc.cu -- tensor-core matcher (SPVO_MATCHER_TENSOR): tcgen05 / TMEM / TMA on sm_100a.
+//
+// Same contract and same results as match.cu (the exact fp32 anchor) -- cv::BFMatcher(NORM_L2)
+// semantics of FeatureFrontEnd::matchDescriptors (reference: src/odml_visual_odometry/src/
+// feature_detection_base.cpp:434-500) -- but the N x M x 256 contraction runs on the 5th-gen
+// tensor cores:
+//
+//   k_tc_prep    fp32 descriptors -> bf16 rows + fp32 squared norms in a row-padded workspace
+//   k_tc_gemm    per (directed problem, 128-row block): S = A . B^T with tcgen05.mma
+//                (cta_group::1, M = N = 128, K = 16, bf16 x bf16 -> fp32 in TMEM), operands staged by
+//                TMA (128 B swizzle) through a 2-stage mbarrier pipeline, accumulators double
+//                buffered in TMEM; the epilogue warps read TMEM with tcgen05.ld and keep, per row,
+//                the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN REGISTERS
+//                (the distance matrix never exists in memory)
+//   k_tc_rerank  exact re-rank: every shortlisted column within a proved error bound of the row
+//                minimum gets its distance recomputed in OpenCV's fp32 operation order (bit-exact
+//                DMatch.distance, first-index ties); rows whose shortlist cannot be proved complete
+//                fall back to an exact scan of the whole row.  Match indices therefore stay
+//                bit-exact although the GEMM is bf16.
+//
+// Error bound.  bf16 rounding (RN) has relative error <= 2^-9 per element, so
+// |a.b - bf16(a).bf16(b)| <= (2^-8 + 2^-18)|a||b|; fp32 accumulation of 256 exact products adds
+// <= 256 * 2^-22 |a||b|.  With eps = kEpsRel*|a||b| + kEpsAbs*(|a|^2+|b|^2) (kEpsRel = 0.0085 covers
+// 2x the dot-product bound), |approx d^2 - exact d^2| <= eps.  A column whose approx d^2 exceeds the
+// row minimum by more than 2*eps cannot be the exact minimum (nor tie with it).
+//
+// Cross-check needs the reverse nearest neighbour as well: it is a second directed problem
+// (B against A) in the same launch; D(a,b) is bitwise symmetric in OpenCV's arithmetic.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace spvo {
+
+constexpr int kDim = SPVO_DESC_DIM;       // 256
+constexpr int kBM = 128, kBN = 128;       // CTA tile: 128 rows of A x 128 rows of B
+constexpr int kKB = 64;                   // k-block = one 128-byte swizzle atom of bf16
+constexpr int kNumKB = kDim / kKB;        // 4
+constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) block
+constexpr int kStages = 2;
+constexpr int kTop = 3;
+constexpr int kTcThreads = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr float kEpsRel = 0.0085f, kEpsAbs = 1e-5f;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B
+// apart (SBO), start address / 16 in the low 14 bits, descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128 (>>3), M = 128 (>>4).
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_prep: operand o = 2p (query of problem p) or 2p+1 (train).  One warp per workspace row.
+// Rows >= n are zero with norm = +inf, so padded columns never enter a shortlist.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb, float* __restrict__ nrm,
+          unsigned* __restrict__ opmax, int cap) {
+  const int o = blockIdx.y, p = o >> 1;
+  const MatchProblem pr = probs[p];
+  const float* src = (o & 1) ? pr.t : pr.q;
+  const int n = (o & 1) ? pr.M : pr.N;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= cap) return;
+  const size_t row = (size_t)o * cap + r;
+  uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+  float s = 0.0f;
+  if (r < n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kDim) + 2 * lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kDim) + 2 * lane + 1);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    packed.x = *reinterpret_cast<uint32_t*>(&h0);
+    packed.y = *reinterpret_cast<uint32_t*>(&h1);
+    packed.z = *reinterpret_cast<uint32_t*>(&h2);
+    packed.w = *reinterpret_cast<uint32_t*>(&h3);
+    s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  reinterpret_cast<uint4*>(xb + row * kDim)[lane] = packed;
+  if (lane == 0) {
+    nrm[row] = r < n ? s : INFINITY;
+    if (r < n) atomicMax(&opmax[o], __float_as_uint(s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_gemm
+// ------------------------------------------------------------------------------------------------
+struct __align__(8) TcShared {
+  uint64_t a_full;
+  uint64_t b_full[kStages], b_empty[kStages];
+  uint64_t acc_full[kStages], acc_empty[kStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void top3_insert(float g, int j, float (&v)[kTop], int (&ix)[kTop]) {
+  if (g < v[2]) {
+    if (g < v[1]) {
+      v[2] = v[1]; ix[2] = ix[1];
+      if (g < v[0]) {
+        v[1] = v[0]; ix[1] = ix[0];
+        v[0] = g; ix[0] = j;
+      } else {
+        v[1] = g; ix[1] = j;
+      }
+    } else {
+      v[2] = g; ix[2] = j;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs, int P,
+          const float* __restrict__ nrm, float* __restrict__ top_val, int* __restrict__ top_idx, int cap) {
+  extern __shared__ uint8_t smem_raw[];
+  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
+  const bool rev = dp >= P;
+  const MatchProblem pr = probs[p];
+  const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
+  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const int rb = blockIdx.x;
+  if (rb * kBM >= Na) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+  const int nct = (Nb + kBN - 1) / kBN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // carve shared memory: operands need 1024 B alignment for the 128 B swizzle
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                                    // 4 x 16 KB
+  const uint32_t sB = base + kNumKB * kTileBytes;              // kStages x 4 x 16 KB
+  TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (sB + kStages * kNumKB * kTileBytes - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&sh->a_full), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&sh->b_full[s]), 1);
+      mbar_init(smem_u32(&sh->b_empty[s]), 1);
+      mbar_init(smem_u32(&sh->acc_full[s]), 1);
+      mbar_init(smem_u32(&sh->acc_empty[s]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulator stages x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"(kStages * kBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0 && nct > 0) {
+      const int a_row = a_op * cap + rb * kBM;
+      mbar_expect_tx(smem_u32(&sh->a_full), kNumKB * kTileBytes);
+      for (int kb = 0; kb < kNumKB; ++kb) tma_load_2d(sA + kb * kTileBytes, &tmap, smem_u32(&sh->a_full), kb * kKB, a_row);
+      for (int ct = 0; ct < nct; ++ct) {
+        const int s = ct % kStages, ph = (ct / kStages) & 1;
+        mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
+        mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes);
+        const int b_row = b_op * cap + ct * kBN;
+        for (int kb = 0; kb < kNumKB; ++kb)
+          tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0 && nct > 0) {
+      mbar_wait(smem_u32(&sh->a_full), 0);
+      for (int ct = 0; ct < nct; ++ct) {
+        const int s = ct % kStages, ph = (ct / kStages) & 1;
+        mbar_wait(smem_u32(&sh->acc_empty[s]), ph ^ 1);  // epilogue drained this accumulator
+        mbar_wait(smem_u32(&sh->b_full[s]), ph);         // TMA landed this B stage
+        tc_fence_after();
+        const uint32_t d = tmem_base + s * kBN;
+#pragma unroll
+        for (int kb = 0; kb < kNumKB; ++kb) {
+#pragma unroll
+          for (int k = 0; k < kKB / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
+            const uint64_t bd = umma_desc_sw128(sB + (s * kNumKB + kb) * kTileBytes + k * 32);
+            tc_mma_bf16(d, ad, bd, kIdesc, (kb | k) != 0);
+          }
+        }
+        tc_commit(smem_u32(&sh->b_empty[s]));   // smem stage free once these MMAs retire
+        tc_commit(smem_u32(&sh->acc_full[s]));  // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int row = rb * kBM + quad * 32 + lane;
+    float v[kTop] = {INFINITY, INFINITY, INFINITY};
+    int ix[kTop] = {-1, -1, -1};
+    const float* nb = nrm + (size_t)b_op * cap;
+    for (int ct = 0; ct < nct; ++ct) {
+      const int s = ct % kStages, ph = (ct / kStages) & 1;
+      mbar_wait(smem_u32(&sh->acc_full[s]), ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + s * kBN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        const int j0 = ct * kBN + c * 32;
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nb + j0) + e4);
+          const float g0 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 0]), n4.x);
+          const float g1 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 1]), n4.y);
+          const float g2 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 2]), n4.z);
+          const float g3 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 3]), n4.w);
+          top3_insert(g0, j0 + 4 * e4 + 0, v, ix);
+          top3_insert(g1, j0 + 4 * e4 + 1, v, ix);
+          top3_insert(g2, j0 + 4 * e4 + 2, v, ix);
+          top3_insert(g3, j0 + 4 * e4 + 3, v, ix);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh->acc_empty[s]));
+    }
+    if (row < Na) {
+      const size_t o = ((size_t)dp * cap + row) * kTop;
+#pragma unroll
+      for (int k = 0; k < kTop; ++k) {
+        top_val[o + k] = v[k];
+        top_idx[o + k] = ix[k];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kStages * kBN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_rerank: one warp per row of a directed problem.  Two (row, column) pairs are evaluated at a
+// time, 16 lanes each: lane (k = l16/4, l = l16%4) owns OpenCV's accumulator s[k][l].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_dist_half(const float* __restrict__ a, const float* __restrict__ b, int l16) {
+  float s = 0.0f;
+#pragma unroll
+  for (int blk = 0; blk < kDim / 16; ++blk) {
+    const float t = __fsub_rn(__ldg(a + blk * 16 + l16), __ldg(b + blk * 16 + l16));
+    s = __fadd_rn(s, __fmul_rn(t, t));
+  }
+  // v[l] = ((s[0][l] + s[1][l]) + s[2][l]) + s[3][l]; lanes hold s[k][l] at l16 = 4k + l
+  const int l = l16 & 3, hb = threadIdx.x & 16;
+  const float s0 = __shfl_sync(0xffffffffu, s, hb + l), s1 = __shfl_sync(0xffffffffu, s, hb + 4 + l);
+  const float s2 = __shfl_sync(0xffffffffu, s, hb + 8 + l), s3 = __shfl_sync(0xffffffffu, s, hb + 12 + l);
+  const float vl = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+  const float v0 = __shfl_sync(0xffffffffu, vl, hb + 0), v1 = __shfl_sync(0xffffffffu, vl, hb + 1);
+  const float v2 = __shfl_sync(0xffffffffu, vl, hb + 2), v3 = __shfl_sync(0xffffffffu, vl, hb + 3);
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(v0, v2), __fadd_rn(v1, v3)));
+}
+
+__device__ __forceinline__ bool lex_less2(float d1, int i1, float d2, int i2) {
+  return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+__device__ __forceinline__ void top2_push(float d, int j, float& b0, int& x0, float& b1, int& x1) {
+  if (lex_less2(d, j, b0, x0)) {
+    b1 = b0; x1 = x0; b0 = d; x0 = j;
+  } else if (lex_less2(d, j, b1, x1)) {
+    b1 = d; x1 = j;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
+            const unsigned* __restrict__ opmax, const float* __restrict__ top_val, const int* __restrict__ top_idx,
+            int cap, int max_rows, int max_cols, int* __restrict__ row_best, float* __restrict__ row_d,
+            int* __restrict__ col_best, unsigned long long* __restrict__ counters) {
+  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
+  const bool rev = dp >= P;
+  const MatchProblem pr = probs[p];
+  const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
+  const float* A = rev ? pr.t : pr.q;
+  const float* B = rev ? pr.q : pr.t;
+  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  if (i >= Na) return;
+  float b0 = INFINITY, b1 = INFINITY;
+  int x0 = INT_MAX, x1 = INT_MAX;
+  bool full = false;
+  const float* arow = A + (size_t)i * kDim;
+  if (Nb > 0) {
+    const size_t o = ((size_t)dp * cap + i) * kTop;
+    float g[kTop];
+    int jx[kTop];
+#pragma unroll
+    for (int k = 0; k < kTop; ++k) {
+      g[k] = top_val[o + k];
+      jx[k] = top_idx[o + k];
+    }
+    const float na = nrm[(size_t)a_op * cap + i], nbmax = __uint_as_float(opmax[b_op]);
+    const float eps = kEpsRel * sqrtf(na * nbmax) + kEpsAbs * (na + nbmax);
+    const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
+    // shortlist size nc: every column that could be the exact minimum (or, for kNN, the exact top two)
+    int nc;
+    if (Nb <= kTop) {
+      nc = Nb;  // the shortlist is the whole row
+    } else if (!knn) {
+      nc = 1;
+      while (nc < kTop && g[nc] <= g[0] + 2.0f * eps) ++nc;
+      if (nc == kTop) full = true;  // the third entry is still within the bound: cannot prove completeness
+    } else {
+      nc = 2;
+      while (nc < kTop && g[nc] <= g[1] + 2.0f * eps) ++nc;
+      if (nc == kTop) {
+        // exact second best unknown; the ratio decision may still be provable from the bound
+        if (g[1] > g[0] + 2.0f * eps) {
+          const float d0 = exact_dist_half(arow, B + (size_t)jx[0] * kDim, l16);
+          const float lo = sqrtf(fmaxf(g[1] + na - eps, 0.0f)) * (1.0f - 1e-6f);
+          const float hi = sqrtf(fmaxf(g[1] + na + eps, 0.0f)) * (1.0f + 1e-6f);
+          if (d0 < ratio * lo) {  // passes for any admissible second best
+            b0 = d0; x0 = jx[0]; b1 = INFINITY; x1 = jx[1];
+            nc = 0;
+          } else if (d0 >= ratio * hi) {  // fails for any admissible second best
+            b0 = d0; x0 = jx[0]; b1 = 0.0f; x1 = jx[1];
+            nc = 0;
+          } else {
+            full = true;
+          }
+        } else {
+          full = true;
+        }
+      }
+    }
+    if (full) {
+      for (int j = half; j < Nb + half; j += 2) {  // both halves iterate the same trip count
+        const int jj = j < Nb ? j : Nb - 1;
+        const float d = exact_dist_half(arow, B + (size_t)jj * kDim, l16);
+        if (j < Nb) top2_push(d, j, b0, x0, b1, x1);
+      }
+    } else {
+      for (int c = half; c < nc + half; c += 2) {
+        const int cc = c < nc ? c : nc - 1;
+        const float d = exact_dist_half(arow, B + (size_t)jx[cc] * kDim, l16);
+        if (c < nc) top2_push(d, jx[cc], b0, x0, b1, x1);
+      }
+    }
+    // merge the two halves
+    const float c0 = __shfl_xor_sync(0xffffffffu, b0, 16), c1 = __shfl_xor_sync(0xffffffffu, b1, 16);
+    const int y0 = __shfl_xor_sync(0xffffffffu, x0, 16), y1 = __shfl_xor_sync(0xffffffffu, x1, 16);
+    if (y0 != x0 || c0 != b0) {
+      top2_push(c0, y0, b0, x0, b1, x1);
+      if (y1 != x1 || c1 != b1) top2_push(c1, y1, b0, x0, b1, x1);
+    } else if (lex_less2(c1, y1, b1, x1)) {
+      b1 = c1; x1 = y1;
+    }
+  }
+  if (lane == 0) {
+    if (!rev) {
+      const size_t o = ((size_t)p * max_rows + i) * 2;
+      row_best[o] = x0 == INT_MAX ? -1 : x0;
+      row_best[o + 1] = x1 == INT_MAX ? -1 : x1;
+      row_d[o] = b0;
+      row_d[o + 1] = b1;
+    } else {
+      col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
+    }
+    if (full) atomicAdd(&counters[1], 1ull);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  }
+  return fn;
+}
+
+struct TcWorkspace {
+  __nv_bfloat16* xb = nullptr;
+  float* nrm = nullptr;
+  unsigned* opmax = nullptr;
+  float* top_val = nullptr;
+  int* top_idx = nullptr;
+  size_t rows = 0, ops = 0, top_rows = 0;
+  CUtensorMap tmap;
+};
+
+static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, size_t ndir) {
+  const size_t rows = ops * cap;
+  cudaError_t e;
+  if (w->rows < rows || w->ops < ops) {
+    if (w->xb) cudaFree(w->xb);
+    if (w->nrm) cudaFree(w->nrm);
+    if (w->opmax) cudaFree(w->opmax);
+    w->xb = nullptr; w->nrm = nullptr; w->opmax = nullptr; w->rows = 0; w->ops = 0;
+    if ((e = cudaMalloc((void**)&w->xb, rows * kDim * sizeof(__nv_bfloat16))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->nrm, rows * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->opmax, ops * sizeof(unsigned))) != cudaSuccess) return e;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)kDim * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&w->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w->xb, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    w->rows = rows;
+    w->ops = ops;
+  }
+  const size_t top_rows = ndir * cap;
+  if (w->top_rows < top_rows) {
+    if (w->top_val) cudaFree(w->top_val);
+    if (w->top_idx) cudaFree(w->top_idx);
+    w->top_val = nullptr; w->top_idx = nullptr; w->top_rows = 0;
+    if ((e = cudaMalloc((void**)&w->top_val, top_rows * kTop * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->top_idx, top_rows * kTop * sizeof(int))) != cudaSuccess) return e;
+    w->top_rows = top_rows;
+  }
+  return cudaSuccess;
+}
+
+void tc_workspace_free(Handle* h) {
+  TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+  if (!w) return;
+  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_val, w->top_idx};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete w;
+  h->tc_ws = nullptr;
+}
+
+cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, int mr, int mc,
+                                 const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride);
+cudaError_t ensure_select_buffers(Handle* h, int P, int mr, int mc);
+
+cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride) {
+  cudaStream_t st = h->stream;
+  cudaError_t e;
+  if (P == 0) return cudaSuccess;
+  const int mr = max_rows > 0 ? max_rows : 1, mc = max_cols > 0 ? max_cols : 1;
+  if ((e = ensure_select_buffers(h, P, mr, mc)) != cudaSuccess) return e;
+  if (max_rows > 0 && max_cols > 0) {
+    if (!h->tc_ws) h->tc_ws = new TcWorkspace();
+    TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+    const int mx = max_rows > max_cols ? max_rows : max_cols;
+    const int cap = (mx + kBM - 1) / kBM * kBM;
+    const bool cross = cfg.mode == SPVO_MATCH_NN_CROSSCHECK;
+    const int ndir = cross ? 2 * P : P;
+    if ((e = tc_ensure(h, w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
+    {
+      LaunchScope ls(h, KID_TC_PREP);
+      k_tc_prep<<<dim3(cap / 8, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap);
+    }
+    const size_t smem = 1024 + (size_t)(1 + kStages) * kNumKB * kTileBytes + sizeof(TcShared);
+    if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    {
+      LaunchScope ls(h, KID_TC_GEMM);
+      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->top_val, w->top_idx, cap);
+    }
+    {
+      LaunchScope ls(h, KID_TC_RERANK);
+      k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_val,
+                                                     w->top_idx, cap, mr, mc, h->row_best, h->row_d, h->col_best,
+                                                     h->counters);
+    }
+  }
+  return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
+}
+
+}  // namespace spvo

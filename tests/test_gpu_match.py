@@ -8,6 +8,7 @@ from conftest import unit_rows
 pytestmark = pytest.mark.gpu
 
 MODES = [0, 1, 2]
+ALGS = [1, 2]  # SPVO_MATCHER_EXACT_FP32, SPVO_MATCHER_TENSOR (tcgen05)
 
 
 def _noisy_copy(a, seed, noise=0.05, perm=True):
@@ -32,32 +33,35 @@ def _check(fe, O, q, t, mode, algorithm=0):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("N,M", [(1000, 1000), (777, 1023), (33, 2048), (1, 1), (2, 1), (500, 3)])
-def test_match_parity_structured(spvo, oracle, mode, N, M):
+@pytest.mark.parametrize("alg", ALGS)
+def test_match_parity_structured(spvo, oracle, mode, N, M, alg):
     fe = spvo.Frontend(0, 1, 64, 64, 16)
     base = unit_rows(max(N, M), seed=N * 7 + M)
     q = base[:N]
     t = _noisy_copy(base, seed=3)[:M]
-    gm = _check(fe, oracle, q, t, mode)
+    gm = _check(fe, oracle, q, t, mode, alg)
     if mode == 2 and N >= 500 and M >= 500:
         assert len(gm) > 100  # ratio test is non-degenerate on structured data
     fe.close()
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_match_parity_random(spvo, oracle, mode):
+@pytest.mark.parametrize("alg", ALGS)
+def test_match_parity_random(spvo, oracle, mode, alg):
     fe = spvo.Frontend(0, 1, 64, 64, 16)
-    _check(fe, oracle, unit_rows(600, 1), unit_rows(640, 2), mode)
+    _check(fe, oracle, unit_rows(600, 1), unit_rows(640, 2), mode, alg)
     fe.close()
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_match_ties_lowest_index_wins(spvo, oracle, mode):
+@pytest.mark.parametrize("alg", ALGS)
+def test_match_ties_lowest_index_wins(spvo, oracle, mode, alg):
     fe = spvo.Frontend(0, 1, 64, 64, 16)
     q, t = unit_rows(200, 11), unit_rows(220, 12)
     t[50] = t[7]; t[120] = t[7]; t[121] = t[7]     # duplicate train rows
     q[30] = q[4]; q[31] = q[4]                     # duplicate query rows
     t[7] = q[4]                                    # an exact zero distance, shared
-    _check(fe, oracle, q, t, mode)
+    _check(fe, oracle, q, t, mode, alg)
     fe.close()
 
 
@@ -73,7 +77,8 @@ def test_match_empty_inputs(spvo):
     fe.close()
 
 
-def test_match_batch_device(spvo, oracle):
+@pytest.mark.parametrize("alg", ALGS)
+def test_match_batch_device(spvo, oracle, alg):
     """Batched device API: slots as written by decode, per-slot row counts read on the device."""
     import torch
     fe = spvo.Frontend(0, 1, 64, 64, 16)
@@ -93,7 +98,7 @@ def test_match_batch_device(spvo, oracle):
         out = torch.zeros(P, stride, 4, dtype=torch.int32, device="cuda")
         nm = torch.zeros(P, dtype=torch.int32, device="cuda")
         q2t = torch.zeros(P, stride, dtype=torch.int32, device="cuda")
-        fe.match_batch_device(d, n_rows, stride, qs, ts, P, stride, out, nm, q2t, mode=mode)
+        fe.match_batch_device(d, n_rows, stride, qs, ts, P, stride, out, nm, q2t, mode=mode, algorithm=alg)
         torch.cuda.synchronize()
         out_h = out.cpu().numpy().view(spvo.DMATCH_DTYPE).reshape(P, stride)
         for p in range(P):
@@ -105,4 +110,25 @@ def test_match_batch_device(spvo, oracle):
             assert (g["queryIdx"] == om["queryIdx"]).all() and (g["trainIdx"] == om["trainIdx"]).all()
             assert (g["distance"].view(np.uint32) == om["distance"].view(np.uint32)).all()
             assert (q2t[p, : rows[a]].cpu().numpy() == omap).all()
+    fe.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("N,M", [(2048, 2048), (4096, 3000), (129, 257)])
+def test_match_tensor_large(spvo, oracle, mode, N, M):
+    """Config 5 sizes through the tcgen05 path; the oracle is the checker."""
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    base = unit_rows(max(N, M), seed=N + M)
+    _check(fe, oracle, base[:N], _noisy_copy(base, seed=8)[:M], mode, 2)
+    fe.close()
+
+
+def test_match_tensor_random_uses_fallback_and_stays_exact(spvo, oracle):
+    """Unstructured descriptors: many rows cannot be proved from the bf16 shortlist and take the
+    exact full-row fallback; results must not change."""
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    q, t = unit_rows(1500, 21), unit_rows(1400, 22)
+    for mode in MODES:
+        _check(fe, oracle, q, t, mode, 2)
+    print("fallback rows:", fe.debug_counters()[1])
     fe.close()
