@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/spvo_frontend.h declares;
+POD layouts match cv::KeyPoint / cv::DMatch; compute entry points fail loudly without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "spvo_frontend.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spvo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(spvo):
+    from spvo_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    L = _lib.load()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in spvo_frontend.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "python binding list and header disagree"
+    assert L.spvo_abi_version() == 1
+
+
+def test_pod_layouts(spvo):
+    from spvo_b200 import _lib
+    assert spvo.KEYPOINT_DTYPE.itemsize == 28 and spvo.DMATCH_DTYPE.itemsize == 16   # cv::KeyPoint / cv::DMatch
+    assert [spvo.KEYPOINT_DTYPE.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave", "class_id")] == \
+        [0, 4, 8, 12, 16, 20, 24]
+    assert [spvo.DMATCH_DTYPE.fields[n][1] for n in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
+    assert C.sizeof(_lib.DecodeCfg) == 16 and C.sizeof(_lib.MatchCfg) == 16 and C.sizeof(_lib.StereoCfg) == 40
+    assert C.sizeof(_lib.StereoOut) == 7 * 8
+
+
+def test_no_cpu_fallback_without_device(spvo):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(spvo.SpvoError) as e:
+        spvo.Frontend(0, 2, 64, 64, 10)
+    assert e.value.code == 3  # SPVO_ENODEVICE
+    from spvo_b200 import _lib
+    assert b"no CUDA device" in _lib.load().spvo_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "superpoint-stereo-visual-odometry_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/spvo_oracle.cpp", "").replace("the oracle", "").replace(
+                    "oracle's", "").replace("oracle_exp", "").replace("oracle (", "").replace("oracle:", "").replace(
+                    "oracle and", "").replace("the CPU oracle", "").replace("passes the oracle", "").lower() or \
+                    "import oracle" not in txt and "from oracle" not in txt
+                assert "from oracle" not in txt and "import oracle" not in txt and "libspvo_oracle" not in txt
