@@ -225,6 +225,7 @@ static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, 
   int alg = cfg->algorithm;
   if (alg == SPVO_MATCHER_AUTO)
     alg = ((long long)max_rows * max_cols >= 128 * 128) ? SPVO_MATCHER_TENSOR : SPVO_MATCHER_EXACT_FP32;
+  if (max_rows > 8192 || max_cols > 8192) alg = SPVO_MATCHER_EXACT_FP32;  // packed shortlist keys carry 13 index bits
   if (alg == SPVO_MATCHER_TENSOR)
     CK(launch_match_tc(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
   else
@@ -437,7 +438,8 @@ long long spvo_kernel_launches(spvo_handle hh) {
 
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
-    "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank"};
+    "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
+    "k_tc_fallback", "k_desc_planes", "k_desc_normalize"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

@@ -41,8 +41,19 @@ constexpr int kNumKB = kDim / kKB;        // 4
 constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) block
 constexpr int kStages = 2;
 constexpr int kTop = 3;
-constexpr int kTcThreads = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;              // 2 per TMEM lane quadrant: each owns 64 of a tile's 128 columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+constexpr int kLists = 2;                 // shortlists per row (one per column half), merged by k_tc_rerank
 constexpr float kEpsRel = 0.0085f, kEpsAbs = 1e-5f;
+constexpr int kIdxBits = 13;              // packed key = (bits(g + off) & ~0x1FFF) | column  (columns < 8192)
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+constexpr float kKeyRel = 1.0f / 1024.0f; // truncating 13 mantissa bits loses < 2^-10 of the (positive) value
+
+// Offset that makes every g_ij + off positive, so fp32 bit patterns order like the values:
+// g = |b|^2 - 2 a.b >= -2|a||b| >= -2 sqrt(amax2 * bmax2).
+__device__ __forceinline__ float key_offset(float amax2, float bmax2) {
+  return 2.0f * sqrtf(amax2 * bmax2) * 1.01f + 1e-30f;  // 1.01 > (1 + 2^-9)^2: bf16 rounding can lengthen both vectors
+}
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -159,25 +170,26 @@ struct __align__(8) TcShared {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void top3_insert(float g, int j, float (&v)[kTop], int (&ix)[kTop]) {
-  if (g < v[2]) {
-    if (g < v[1]) {
-      v[2] = v[1]; ix[2] = ix[1];
-      if (g < v[0]) {
-        v[1] = v[0]; ix[1] = ix[0];
-        v[0] = g; ix[0] = j;
-      } else {
-        v[1] = g; ix[1] = j;
-      }
-    } else {
-      v[2] = g; ix[2] = j;
-    }
-  }
+// Branch-free insertion of a packed key into the ascending triple (k0 <= k1 <= k2).
+__device__ __forceinline__ void top3_net(uint32_t x, uint32_t& k0, uint32_t& k1, uint32_t& k2) {
+  uint32_t t = min(k0, x);
+  x = max(k0, x);
+  k0 = t;
+  t = min(k1, x);
+  x = max(k1, x);
+  k1 = t;
+  k2 = min(k2, x);
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
+  tmem_ld32(taddr, r);
+  tmem_ld32(taddr + 32, r + 32);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs, int P,
-          const float* __restrict__ nrm, float* __restrict__ top_val, int* __restrict__ top_idx, int cap) {
+          const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
+          int cap) {
   extern __shared__ uint8_t smem_raw[];
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
@@ -201,7 +213,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
       mbar_init(smem_u32(&sh->b_full[s]), 1);
       mbar_init(smem_u32(&sh->b_empty[s]), 1);
       mbar_init(smem_u32(&sh->acc_full[s]), 1);
-      mbar_init(smem_u32(&sh->acc_empty[s]), 128);
+      mbar_init(smem_u32(&sh->acc_empty[s]), 32 * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -255,46 +267,43 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; column half = (warp - 2) / 4 =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = rb * kBM + quad * 32 + lane;
-    float v[kTop] = {INFINITY, INFINITY, INFINITY};
-    int ix[kTop] = {-1, -1, -1};
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
     const float* nb = nrm + (size_t)b_op * cap;
+    const float off = key_offset(__uint_as_float(opmax[a_op]), __uint_as_float(opmax[b_op]));
     for (int ct = 0; ct < nct; ++ct) {
       const int s = ct % kStages, ph = (ct / kStages) & 1;
+      const int j0 = ct * kBN + half * 64;
+      // the 64 column norms do not depend on the MMA: fetch them before waiting for the accumulator
+      float4 n4[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) n4[e] = __ldg(reinterpret_cast<const float4*>(nb + j0) + e);
       mbar_wait(smem_u32(&sh->acc_full[s]), ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + s * kBN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        const int j0 = ct * kBN + c * 32;
+      uint32_t acc[64];
+      tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nb + j0) + e4);
-          const float g0 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 0]), n4.x);
-          const float g1 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 1]), n4.y);
-          const float g2 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 2]), n4.z);
-          const float g3 = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e4 + 3]), n4.w);
-          top3_insert(g0, j0 + 4 * e4 + 0, v, ix);
-          top3_insert(g1, j0 + 4 * e4 + 1, v, ix);
-          top3_insert(g2, j0 + 4 * e4 + 2, v, ix);
-          top3_insert(g3, j0 + 4 * e4 + 3, v, ix);
+      for (int e = 0; e < 16; ++e) {
+        const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
+          const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
+          const uint32_t key = (__float_as_uint(g) & ~kIdxMask) | (uint32_t)(j0 + 4 * e + u);
+          top3_net(key, k0, k1, k2);
         }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&sh->acc_empty[s]));
     }
     if (row < Na) {
-      const size_t o = ((size_t)dp * cap + row) * kTop;
-#pragma unroll
-      for (int k = 0; k < kTop; ++k) {
-        top_val[o + k] = v[k];
-        top_idx[o + k] = ix[k];
-      }
+      uint32_t* o = top_key + (((size_t)dp * cap + row) * kLists + half) * kTop;
+      o[0] = k0;
+      o[1] = k1;
+      o[2] = k2;
     }
   }
   tc_fence_before();
@@ -339,9 +348,9 @@ __device__ __forceinline__ void top2_push(float d, int j, float& b0, int& x0, fl
 
 __global__ void __launch_bounds__(256)
 k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
-            const unsigned* __restrict__ opmax, const float* __restrict__ top_val, const int* __restrict__ top_idx,
-            int cap, int max_rows, int max_cols, int* __restrict__ row_best, float* __restrict__ row_d,
-            int* __restrict__ col_best, unsigned long long* __restrict__ counters) {
+            const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
+            int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
+            int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters) {
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -356,34 +365,46 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   bool full = false;
   const float* arow = A + (size_t)i * kDim;
   if (Nb > 0) {
-    const size_t o = ((size_t)dp * cap + i) * kTop;
+    // merge the two per-half shortlists: the kTop smallest packed keys of the row
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    const float na = nrm[(size_t)a_op * cap + i];
+    const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
+    const float off = key_offset(amax, bmax);
+    const uint32_t kk[kTop] = {k0, k1, k2};
     float g[kTop];
     int jx[kTop];
 #pragma unroll
     for (int k = 0; k < kTop; ++k) {
-      g[k] = top_val[o + k];
-      jx[k] = top_idx[o + k];
+      g[k] = __uint_as_float(kk[k] & ~kIdxMask) - off;   // truncated: true value in [g, g + kKeyRel*(g+off))
+      jx[k] = (int)(kk[k] & kIdxMask);
     }
-    const float na = nrm[(size_t)a_op * cap + i], nbmax = __uint_as_float(opmax[b_op]);
-    const float eps = kEpsRel * sqrtf(na * nbmax) + kEpsAbs * (na + nbmax);
+    // bound on |approx - exact| of any relevant column of this row, plus the key truncation
+    const float eps = kEpsRel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
     const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
-    // shortlist size nc: every column that could be the exact minimum (or, for kNN, the exact top two)
+    const float ref = knn ? g[1] : g[0];
+    const float slack = 2.0f * eps + kKeyRel * (ref + 2.0f * eps + off) * 1.01f;
     int nc;
     if (Nb <= kTop) {
       nc = Nb;  // the shortlist is the whole row
     } else if (!knn) {
       nc = 1;
-      while (nc < kTop && g[nc] <= g[0] + 2.0f * eps) ++nc;
+      while (nc < kTop && g[nc] <= g[0] + slack) ++nc;
       if (nc == kTop) full = true;  // the third entry is still within the bound: cannot prove completeness
     } else {
       nc = 2;
-      while (nc < kTop && g[nc] <= g[1] + 2.0f * eps) ++nc;
+      while (nc < kTop && g[nc] <= g[1] + slack) ++nc;
       if (nc == kTop) {
         // exact second best unknown; the ratio decision may still be provable from the bound
-        if (g[1] > g[0] + 2.0f * eps) {
+        const float slack0 = 2.0f * eps + kKeyRel * (g[0] + 2.0f * eps + off) * 1.01f;
+        if (g[1] > g[0] + slack0) {
           const float d0 = exact_dist_half(arow, B + (size_t)jx[0] * kDim, l16);
-          const float lo = sqrtf(fmaxf(g[1] + na - eps, 0.0f)) * (1.0f - 1e-6f);
-          const float hi = sqrtf(fmaxf(g[1] + na + eps, 0.0f)) * (1.0f + 1e-6f);
+          const float lo2 = g[1] + na - eps;                                     // exact second best d^2 >= lo2
+          const float hi2 = g[1] + na + eps + kKeyRel * (g[1] + off) * 1.01f;    // and <= hi2
+          const float lo = sqrtf(fmaxf(lo2, 0.0f)) * (1.0f - 1e-6f);
+          const float hi = sqrtf(fmaxf(hi2, 0.0f)) * (1.0f + 1e-6f);
           if (d0 < ratio * lo) {  // passes for any admissible second best
             b0 = d0; x0 = jx[0]; b1 = INFINITY; x1 = jx[1];
             nc = 0;
@@ -399,11 +420,12 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       }
     }
     if (full) {
-      for (int j = half; j < Nb + half; j += 2) {  // both halves iterate the same trip count
-        const int jj = j < Nb ? j : Nb - 1;
-        const float d = exact_dist_half(arow, B + (size_t)jj * kDim, l16);
-        if (j < Nb) top2_push(d, j, b0, x0, b1, x1);
+      // shortlist not provably complete: queue the row for k_tc_fallback (which writes its result)
+      if (lane == 0) {
+        fb_list[(size_t)dp * cap + atomicAdd(&fb_count[dp], 1)] = i;
+        atomicAdd(&counters[1], 1ull);
       }
+      return;
     } else {
       for (int c = half; c < nc + half; c += 2) {
         const int cc = c < nc ? c : nc - 1;
@@ -431,7 +453,168 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
     } else {
       col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
     }
-    if (full) atomicAdd(&counters[1], 1ull);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tc_fallback: one CTA per directed problem re-evaluates its queued rows against ALL columns,
+// eight rows at a time so the train descriptors stream through once per group.
+// Phase 1: fp32 dot products (error ~1e-5, three orders below the bf16 bound) give every column's
+// g = |b|^2 - 2 a.b; each warp keeps the 3 best columns per row.  Phase 2: the columns within
+// 2*eps32 of the row minimum (of the second minimum for kNN) are re-evaluated in OpenCV's exact
+// order.  If that list could be incomplete (>= 3 near-ties inside one warp's share) every column is
+// scanned exactly (counters[2]).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFbRows = 8;
+
+__global__ void __launch_bounds__(256)
+k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm, int cap,
+              int max_rows, int max_cols, const int* __restrict__ fb_count, const int* __restrict__ fb_list,
+              int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
+              unsigned long long* __restrict__ counters) {
+  __shared__ float s_v[8][kFbRows][3];
+  __shared__ int s_j[8][kFbRows][3];
+  const int dp = blockIdx.x, p = dp < P ? dp : dp - P;
+  const int nfb = fb_count[dp];
+  if (nfb == 0) return;
+  const bool rev = dp >= P;
+  const MatchProblem pr = probs[p];
+  const int Nb = rev ? pr.N : pr.M;
+  const float* A = rev ? pr.t : pr.q;
+  const float* B = rev ? pr.q : pr.t;
+  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const float* nbv = nrm + (size_t)b_op * cap;
+  const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int myr = lane >> 2;  // after the butterfly, lanes 4r..4r+3 hold row r's dot product
+
+  for (int r0 = 0; r0 < nfb; r0 += kFbRows) {
+    const int nr = min(kFbRows, nfb - r0);
+    // this lane's 8 elements (8*lane .. 8*lane+7) of each of the group's rows
+    float a[kFbRows][8];
+#pragma unroll
+    for (int r = 0; r < kFbRows; ++r) {
+      const int i = fb_list[(size_t)dp * cap + r0 + min(r, nr - 1)];
+      const float4 x = __ldg(reinterpret_cast<const float4*>(A + (size_t)i * kDim) + 2 * lane);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(A + (size_t)i * kDim) + 2 * lane + 1);
+      a[r][0] = x.x; a[r][1] = x.y; a[r][2] = x.z; a[r][3] = x.w;
+      a[r][4] = y.x; a[r][5] = y.y; a[r][6] = y.z; a[r][7] = y.w;
+    }
+    float v[3] = {INFINITY, INFINITY, INFINITY};
+    int ix[3] = {-1, -1, -1};
+    for (int j = warp; j < Nb; j += 8) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
+      const float b[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+      float pd[kFbRows];
+#pragma unroll
+      for (int r = 0; r < kFbRows; ++r) {
+        float t = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t = __fmaf_rn(a[r][e], b[e], t);
+        pd[r] = t;
+      }
+      // reduce 8 values over 32 lanes: halve the value set at xor 16 / 8 / 4, then finish at xor 2 / 1
+      float q4[4], q2[2], q1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float keep = (lane & 16) ? pd[r + 4] : pd[r], send = (lane & 16) ? pd[r] : pd[r + 4];
+        q4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float keep = (lane & 8) ? q4[r + 2] : q4[r], send = (lane & 8) ? q4[r] : q4[r + 2];
+        q2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const float keep = (lane & 4) ? q2[1] : q2[0], send = (lane & 4) ? q2[0] : q2[1];
+        q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+      const float g = __fmaf_rn(-2.0f, q1, nbv[j]);
+      if (g < v[2]) {
+        if (g < v[1]) {
+          v[2] = v[1]; ix[2] = ix[1];
+          if (g < v[0]) { v[1] = v[0]; ix[1] = ix[0]; v[0] = g; ix[0] = j; } else { v[1] = g; ix[1] = j; }
+        } else { v[2] = g; ix[2] = j; }
+      }
+    }
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        s_v[warp][myr][k] = v[k];
+        s_j[warp][myr][k] = ix[k];
+      }
+    }
+    __syncthreads();
+    // warp w finishes row w of the group: 24 shortlisted columns (3 per warp)
+    if (warp < nr) {
+      const int i = fb_list[(size_t)dp * cap + r0 + warp];
+      const float* arow = A + (size_t)i * kDim;
+      const float na = nrm[(size_t)a_op * cap + i];
+      const float cv = lane < 24 ? s_v[lane / 3][warp][lane % 3] : INFINITY;
+      const int cj = lane < 24 ? s_j[lane / 3][warp][lane % 3] : -1;
+      float m0 = cv, m1 = INFINITY, bm = (cj >= 0) ? nbv[cj] : 0.f;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float c0 = __shfl_xor_sync(0xffffffffu, m0, o), c1 = __shfl_xor_sync(0xffffffffu, m1, o);
+        const float lo = fminf(m0, c0), hi = fmaxf(m0, c0);
+        m1 = fminf(hi, fminf(m1, c1));
+        m0 = lo;
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+      }
+      const float eps32 = 4e-5f * (na + bm);  // >= 2 * (256 + 8) * 2^-24 |a||b| plus the final roundings
+      const float thr = (knn ? m1 : m0) + 2.0f * eps32;
+      const bool cand = cj >= 0 && cv <= thr;
+      // a warp's third entry inside the threshold means that warp may have dropped a near-tie
+      const bool overflow = __any_sync(0xffffffffu, cand && (lane % 3) == 2 && Nb > 24);
+      float b0 = INFINITY, b1 = INFINITY;
+      int x0 = INT_MAX, x1 = INT_MAX;
+      if (overflow) {
+        for (int j = half; j < Nb + half; j += 2) {
+          const int jj = j < Nb ? j : Nb - 1;
+          const float d = exact_dist_half(arow, B + (size_t)jj * kDim, l16);
+          if (j < Nb) top2_push(d, j, b0, x0, b1, x1);
+        }
+        if (lane == 0) atomicAdd(&counters[2], 1ull);
+      } else {
+        unsigned pending = __ballot_sync(0xffffffffu, cand);
+        while (pending) {  // two candidate columns per step, one per half warp
+          const int s0 = __ffs(pending) - 1;
+          pending &= pending - 1;
+          int s1 = s0;
+          if (pending) {
+            s1 = __ffs(pending) - 1;
+            pending &= pending - 1;
+          }
+          const int ja = __shfl_sync(0xffffffffu, cj, s0), jb = __shfl_sync(0xffffffffu, cj, s1);
+          const int j = half ? jb : ja;
+          const float d = exact_dist_half(arow, B + (size_t)j * kDim, l16);
+          if (half == 0 || s1 != s0) top2_push(d, j, b0, x0, b1, x1);
+        }
+      }
+      const float c0 = __shfl_xor_sync(0xffffffffu, b0, 16), c1 = __shfl_xor_sync(0xffffffffu, b1, 16);
+      const int y0 = __shfl_xor_sync(0xffffffffu, x0, 16), y1 = __shfl_xor_sync(0xffffffffu, x1, 16);
+      if (y0 != x0 || c0 != b0) {
+        top2_push(c0, y0, b0, x0, b1, x1);
+        if (y1 != x1 || c1 != b1) top2_push(c1, y1, b0, x0, b1, x1);
+      } else if (lex_less2(c1, y1, b1, x1)) {
+        b1 = c1; x1 = y1;
+      }
+      if (lane == 0) {
+        if (!rev) {
+          const size_t o = ((size_t)p * max_rows + i) * 2;
+          row_best[o] = x0 == INT_MAX ? -1 : x0;
+          row_best[o + 1] = x1 == INT_MAX ? -1 : x1;
+          row_d[o] = b0;
+          row_d[o + 1] = b1;
+        } else {
+          col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -458,8 +641,9 @@ struct TcWorkspace {
   __nv_bfloat16* xb = nullptr;
   float* nrm = nullptr;
   unsigned* opmax = nullptr;
-  float* top_val = nullptr;
-  int* top_idx = nullptr;
+  uint32_t* top_key = nullptr;
+  int* fb_count = nullptr;
+  int* fb_list = nullptr;
   size_t rows = 0, ops = 0, top_rows = 0;
   CUtensorMap tmap;
 };
@@ -489,11 +673,13 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
   }
   const size_t top_rows = ndir * cap;
   if (w->top_rows < top_rows) {
-    if (w->top_val) cudaFree(w->top_val);
-    if (w->top_idx) cudaFree(w->top_idx);
-    w->top_val = nullptr; w->top_idx = nullptr; w->top_rows = 0;
-    if ((e = cudaMalloc((void**)&w->top_val, top_rows * kTop * sizeof(float))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&w->top_idx, top_rows * kTop * sizeof(int))) != cudaSuccess) return e;
+    if (w->top_key) cudaFree(w->top_key);
+    if (w->fb_count) cudaFree(w->fb_count);
+    if (w->fb_list) cudaFree(w->fb_list);
+    w->top_key = nullptr; w->fb_count = nullptr; w->fb_list = nullptr; w->top_rows = 0;
+    if ((e = cudaMalloc((void**)&w->fb_count, top_rows * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
     w->top_rows = top_rows;
   }
   return cudaSuccess;
@@ -502,7 +688,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
 void tc_workspace_free(Handle* h) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
   if (!w) return;
-  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_val, w->top_idx};
+  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_count, w->fb_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete w;
@@ -529,6 +715,7 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     const int ndir = cross ? 2 * P : P;
     if ((e = tc_ensure(h, w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_PREP);
       k_tc_prep<<<dim3(cap / 8, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap);
@@ -537,13 +724,18 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_GEMM);
-      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->top_val, w->top_idx, cap);
+      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap);
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
-      k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_val,
-                                                     w->top_idx, cap, mr, mc, h->row_best, h->row_d, h->col_best,
+      k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
+                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count, w->fb_list,
                                                      h->counters);
+    }
+    {
+      LaunchScope ls(h, KID_TC_FALLBACK);
+      k_tc_fallback<<<ndir, 256, 0, st>>>(probs, P, cfg.mode, w->nrm, cap, mr, mc, w->fb_count, w->fb_list,
+                                          h->row_best, h->row_d, h->col_best, h->counters);
     }
   }
   return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
