@@ -111,9 +111,10 @@ __device__ __forceinline__ u64 make_key(uint32_t bits, int x, int y, int H) {
   return ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
 }
 
-// Visit every pixel of the image once (float4 granularity, uniform trip count per warp).
-// f(bits, x, y) is called for the four pixels of each float4; `any` prefilter keeps the common
-// no-candidate case to one vote.
+// Visit every pixel of the image once (float4 granularity, uniform trip count per warp), kScanU
+// independent 16-byte loads in flight per thread.  fn(selected, bits, x, y) is called for the four
+// pixels of a float4 only when some lane of the warp has a selected pixel.
+constexpr int kScanU = 8;
 template <class Pred, class Fn>
 __device__ __forceinline__ void scan_heat(const float* __restrict__ heat, int H, int W, Pred pred, Fn fn) {
   const int n4 = (H * W) >> 2;
@@ -121,24 +122,31 @@ __device__ __forceinline__ void scan_heat(const float* __restrict__ heat, int H,
   const int dy = S / W, dx = S - dy * W;
   int p0 = threadIdx.x * 4;
   int y = p0 / W, x = p0 - y * W;
-  for (int base = 0; base < n4; base += kDetectThreads) {
-    const int i4 = base + threadIdx.x;
-    const bool in = i4 < n4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in) v = __ldg(reinterpret_cast<const float4*>(heat) + i4);
-    const uint32_t b0 = fbits(v.x), b1 = fbits(v.y), b2 = fbits(v.z), b3 = fbits(v.w);
-    const bool s0 = in && pred(b0), s1 = in && pred(b1), s2 = in && pred(b2), s3 = in && pred(b3);
-    if (__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) {
-      fn(s0, b0, x, y);
-      fn(s1, b1, x + 1, y);
-      fn(s2, b2, x + 2, y);
-      fn(s3, b3, x + 3, y);
+  for (int base = 0; base < n4; base += kScanU * kDetectThreads) {
+    float4 v[kScanU];
+#pragma unroll
+    for (int u = 0; u < kScanU; ++u) {
+      const int i4 = base + u * kDetectThreads + threadIdx.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i4 < n4) v[u] = __ldg(reinterpret_cast<const float4*>(heat) + i4);
     }
-    x += dx;
-    y += dy;
-    if (x >= W) {
-      x -= W;
-      ++y;
+#pragma unroll
+    for (int u = 0; u < kScanU; ++u) {
+      const bool in = base + u * kDetectThreads + threadIdx.x < n4;
+      const uint32_t b0 = fbits(v[u].x), b1 = fbits(v[u].y), b2 = fbits(v[u].z), b3 = fbits(v[u].w);
+      const bool s0 = in && pred(b0), s1 = in && pred(b1), s2 = in && pred(b2), s3 = in && pred(b3);
+      if (__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) {
+        fn(s0, b0, x, y);
+        fn(s1, b1, x + 1, y);
+        fn(s2, b2, x + 2, y);
+        fn(s3, b3, x + 3, y);
+      }
+      x += dx;
+      y += dy;
+      if (x >= W) {
+        x -= W;
+        ++y;
+      }
     }
   }
 }
@@ -240,15 +248,29 @@ __device__ void bitonic_sort_desc(u64* keys, int n_pad) {
   }
 }
 
+// Exact greedy NMS, in parallel.  The reference walks candidates in rank order and keeps one iff no
+// earlier-kept candidate lies within its (2d+1)^2 box (NN:229-255).  Equivalently: candidate i is
+// KEPT iff every earlier-rank candidate inside its box is SUPPRESSED, and SUPPRESSED iff one of them
+// is KEPT.  Each round decides every candidate whose earlier-rank box neighbours are all decided;
+// states only move UNDECIDED -> KEPT/SUPPRESSED, so racing reads are harmless and the fixed point is
+// the sequential result.  Neighbours are found through a spatial hash of 8x8-pixel cells (linked
+// lists in shared memory).  Suppression by earlier chunks comes from the bitmap.
+enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
+constexpr uint16_t kNil = 0xFFFFu;
+
 __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
-  const int H = p.H, W = p.W, K = p.K, cap = p.cap;
+  const int H = p.H, W = p.W, K = p.K, cap = p.cap, d = p.dist, bd = p.border;
   const int ww = (W + 31) >> 5;  // bitmap words per row
-  u64* keys = reinterpret_cast<u64*>(smem_raw);                  // [cap]
-  u64* emit = keys + cap;                                        // [K]
-  unsigned* bitmap = reinterpret_cast<unsigned*>(emit + K);      // [H*ww]
-  unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (used before collect)
+  const int Hc = H >> 3, Wc = W >> 3, cells = Hc * Wc;
+  u64* keys = reinterpret_cast<u64*>(smem_raw);                  // [cap]   sorted candidate keys of the chunk
+  u64* emit = keys + cap;                                        // [K]     emitted keypoints (score | y<<16 | x)
+  unsigned* bitmap = reinterpret_cast<unsigned*>(emit + K);      // [H*ww]  pixels suppressed by earlier chunks
+  int* head = reinterpret_cast<int*>(bitmap + H * ww);           // [cells] spatial hash: first candidate of a cell
+  uint16_t* next = reinterpret_cast<uint16_t*>(head + cells);    // [cap]
+  uint8_t* state = reinterpret_cast<uint8_t*>(next + cap);       // [cap]
+  unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
   __shared__ int s_count, s_want, s_bin, s_emitted;
   __shared__ u64 s_prefix;
   __shared__ unsigned s_warp_tot[kDetectThreads / 32];
@@ -258,7 +280,6 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
   const u64 floor_key = ((u64)conf_bits + 1ull) << 32;  // smallest possible candidate key (score > conf)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- zero the suppression bitmap -------------------------------------------------------------
   for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
   if (tid == 0) {
     s_emitted = 0;
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
       if (lo < floor_key) lo = floor_key;
     }
   }
-  __syncthreads();  // s_hist (aliasing keys) no longer needed
+  __syncthreads();
 
   bool slow = false;
   // ---- chunk loop: consume candidates in descending key order ----------------------------------
@@ -328,56 +349,113 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
     int n_pad = 32;
     while (n_pad < n) n_pad <<= 1;
     for (int i = n + tid; i < n_pad; i += kDetectThreads) keys[i] = 0ull;
+    for (int i = tid; i < cells; i += kDetectThreads) head[i] = -1;
     __syncthreads();
     bitonic_sort_desc(keys, n_pad);
 
-    // ---- greedy NMS walk (warp 0), 32 candidates per window -------------------------------------
-    if (warp == 0) {
-      int emitted = s_emitted;
-      const int d = p.dist, bd = p.border;
-      for (int base = 0; base < n && emitted < K; base += 32) {
-        const int idx = base + lane;
-        const bool valid = idx < n;
-        u64 key = valid ? keys[idx] : 0ull;
-        uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
-        int x = valid ? (int)(pos / (uint32_t)H) : -1000000;
-        int y = valid ? (int)(pos - (uint32_t)x * (uint32_t)H) : -1000000;
-        bool supp = !valid;
-        if (valid) supp = (bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u;
-        unsigned alive = __ballot_sync(0xffffffffu, !supp);
-        while (alive && emitted < K) {
-          const int j = __ffs(alive) - 1;
-          const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-          // emit iff inside the border (NN:239-244); a border point still suppresses (NN:246-254)
-          if (yj >= bd && yj + bd < H && xj >= bd && xj + bd < W) {
-            if (lane == j) emit[emitted] = key;
-            ++emitted;
-          }
-          // mark the (2d+1)^2 box, clipped to the image
-          const int x0 = max(xj - d, 0), x1 = min(xj + d, W - 1);
-          for (int r = lane; r < 2 * d + 1; r += 32) {
-            const int yy = yj - d + r;
-            if (yy >= 0 && yy < H) {
-              for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
-                const int lo_b = max(x0 - (w << 5), 0), hi_b = min(x1 - (w << 5), 31);
-                const unsigned mask = (0xffffffffu >> (31 - hi_b)) & (0xffffffffu << lo_b);
-                bitmap[yy * ww + w] |= mask;
-              }
-            }
-          }
-          // candidates of this window inside the new box are suppressed (j itself included)
-          if (abs(x - xj) <= d && abs(y - yj) <= d) supp = true;
-          alive = __ballot_sync(0xffffffffu, !supp) & ~((2u << j) - 1u);
-          __syncwarp();  // box marks of this point are visible before the next point's read-modify-write
-        }
-        __syncwarp();
-      }
-      if (lane == 0) s_emitted = emitted;
+    // ---- A: unpack positions, initial states, spatial hash ---------------------------------------
+    for (int i = tid; i < n; i += kDetectThreads) {
+      const u64 key = keys[i];
+      const uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
+      const int x = (int)(pos / (uint32_t)H), y = (int)(pos - (uint32_t)x * (uint32_t)H);
+      keys[i] = (key & 0xFFFFFFFF00000000ull) | (u64)(((uint32_t)y << 16) | (uint32_t)x);
+      const bool sup = (bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u;
+      state[i] = sup ? ST_SUPP : ST_UNDEC;
+      // d == 0: a point only suppresses its own pixel, nothing interacts
+      if (!sup && d > 0) next[i] = (uint16_t)atomicExch(&head[(y >> 3) * Wc + (x >> 3)], i);
     }
     __syncthreads();
+
+    // ---- B: fixed-point rounds ---------------------------------------------------------------------
+    if (d == 0) {
+      for (int i = tid; i < n; i += kDetectThreads)
+        if (state[i] == ST_UNDEC) state[i] = ST_KEPT;
+      __syncthreads();
+    } else {
+      volatile uint8_t* vstate = state;
+      while (true) {
+        int undecided = 0;
+        for (int i = tid; i < n; i += kDetectThreads) {
+          if (vstate[i] != ST_UNDEC) continue;
+          const uint32_t xy = (uint32_t)keys[i];
+          const int x = xy & 0xFFFF, y = xy >> 16;
+          const int cx0 = max(x - d, 0) >> 3, cx1 = min(x + d, W - 1) >> 3;
+          const int cy0 = max(y - d, 0) >> 3, cy1 = min(y + d, H - 1) >> 3;
+          bool kept = false, undec = false;
+          for (int cy = cy0; cy <= cy1; ++cy)
+            for (int cx = cx0; cx <= cx1; ++cx)
+              for (int q = head[cy * Wc + cx]; q >= 0 && q != kNil; q = next[q]) {
+                if (q < i) {
+                  const uint32_t qxy = (uint32_t)keys[q];
+                  const int qx = qxy & 0xFFFF, qy = qxy >> 16;
+                  if (abs(qx - x) <= d && abs(qy - y) <= d) {
+                    const uint8_t sq = vstate[q];
+                    kept |= sq == ST_KEPT;
+                    undec |= sq == ST_UNDEC;
+                  }
+                }
+              }
+          if (kept) vstate[i] = ST_SUPP;
+          else if (!undec) vstate[i] = ST_KEPT;
+          else ++undecided;
+        }
+        if (__syncthreads_count(undecided > 0) == 0) break;
+      }
+    }
+
+    // ---- C: emit kept in-border candidates in rank order, up to K ------------------------------------
+    {
+      const int seg = (n + kDetectThreads - 1) / kDetectThreads;
+      const int i0 = min(tid * seg, n), i1 = min(i0 + seg, n);
+      int cnt = 0;
+      for (int i = i0; i < i1; ++i) {
+        const uint32_t xy = (uint32_t)keys[i];
+        const int x = xy & 0xFFFF, y = xy >> 16;
+        cnt += (state[i] == ST_KEPT && y >= bd && y + bd < H && x >= bd && x + bd < W) ? 1 : 0;
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) s_warp_tot[warp] = (unsigned)inc;
+      __syncthreads();
+      int off = s_emitted, total = 0;
+      for (int w = 0; w < kDetectThreads / 32; ++w) {
+        if (w < warp) off += (int)s_warp_tot[w];
+        total += (int)s_warp_tot[w];
+      }
+      int slot = off + inc - cnt;
+      for (int i = i0; i < i1; ++i) {
+        const u64 key = keys[i];
+        const uint32_t xy = (uint32_t)key;
+        const int x = xy & 0xFFFF, y = xy >> 16;
+        if (state[i] == ST_KEPT && y >= bd && y + bd < H && x >= bd && x + bd < W) {
+          if (slot < K) emit[slot] = key;
+          ++slot;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_emitted = min(K, s_emitted + total);
+      __syncthreads();
+    }
     if (s_emitted >= K || lo <= floor_key) break;
-    // more candidates are needed: next chunk = the next `cap` keys below lo (exact slow path)
+
+    // ---- D: more candidates are needed: record this chunk's boxes, take the next `cap` keys --------
     slow = true;
+    for (int i = tid; i < n; i += kDetectThreads) {
+      if (state[i] != ST_KEPT) continue;
+      const uint32_t xy = (uint32_t)keys[i];
+      const int xj = xy & 0xFFFF, yj = xy >> 16;
+      const int x0 = max(xj - d, 0), x1 = min(xj + d, W - 1);
+      for (int yy = max(yj - d, 0); yy <= min(yj + d, H - 1); ++yy)
+        for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+          const int lo_b = max(x0 - (w << 5), 0), hi_b = min(x1 - (w << 5), 31);
+          atomicOr(&bitmap[yy * ww + w], (0xffffffffu >> (31 - hi_b)) & (0xffffffffu << lo_b));
+        }
+    }
+    __syncthreads();
     hi = lo;
     lo = radix_select(heat, H, W, conf_bits, hi, cap, floor_key, s_hist, &s_prefix, &s_want);
     __syncthreads();
@@ -391,9 +469,8 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
     float sc = 0.f;
     if (i < n_emit) {
       const u64 key = emit[i];
-      const uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
-      const int x = (int)(pos / (uint32_t)H), y = (int)(pos - (uint32_t)x * (uint32_t)H);
-      o.x = (float)x; o.y = (float)y; o.size = 1.0f; o.angle = -1.0f; o.response = 0.0f;
+      const uint32_t xy = (uint32_t)key;
+      o.x = (float)(xy & 0xFFFF); o.y = (float)(xy >> 16); o.size = 1.0f; o.angle = -1.0f; o.response = 0.0f;
       o.octave = 0; o.class_id = -1;
       sc = __uint_as_float((uint32_t)(key >> 32));
     } else {
@@ -479,7 +556,8 @@ k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   const int ww = (W + 31) >> 5;
-  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4;
+  const size_t cells = (size_t)(H / 8) * (W / 8);
+  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4 + cells * 4 + (size_t)cap * 2 + (size_t)cap;
 }
 
 cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
