@@ -278,6 +278,8 @@ def run_ours(args, rank, world, local_rank):
             "k_softmax_heat": ("hbm", B * 4 * 65 * cells),
             "k_detect": ("hbm", B * K * 28),
             "k_sample_desc": ("hbm", B * (4 * 256 * cells + K * 1024)),
+            "k_desc_planes": ("hbm", B * 4 * 256 * cells),
+            "k_desc_normalize": ("hbm", B * K * 1024),
             "k_dist_exact": ("tensor", 2 * F * 2.0 * n_kp * n_kp * 256),
             "k_tc_gemm": ("tensor", 2 * F * 2.0 * n_kp * n_kp * 256),
         }
@@ -296,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
             ach, peak, unit = work / dur / 1e12, peaks["tf_sus"], "TFLOP/s"
         roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                     "traffic": traffic, "peak_source": peaks["src"] + (" (sustained)" if bound == "tensor" else "")}
-        dec_ms = sum(prof[k][0] for k in ("k_softmax_heat", "k_detect", "k_sample_desc") if k in prof) / args.steps
+        dec_ms = sum(prof[k][0] for k in ("k_softmax_heat", "k_detect", "k_sample_desc", "k_desc_planes", "k_desc_normalize") if k in prof) / args.steps
         dec_bytes = B * (4 * (65 + 256) * cells + K * 1052)
         decode_roofline = {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
                            "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peaks["hbm"],

@@ -109,6 +109,8 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   ALLOC(h->st_desc_out, (size_t)max_batch * K * 256 * sizeof(float));
   ALLOC(h->st_n, (size_t)max_batch * sizeof(int));
   ALLOC(h->st_scores, (size_t)max_batch * K * sizeof(float));
+  ALLOC(h->desc_tmp, (size_t)max_batch * 256 * K * sizeof(float));
+  ALLOC(h->kp_par, (size_t)max_batch * K * sizeof(int4));
   ALLOC(h->probs, 4096 * sizeof(MatchProblem));
   h->probs_cap = 4096;
 #undef ALLOC
@@ -122,7 +124,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
@@ -439,7 +441,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_desc_planes", "k_desc_normalize"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_desc_planes", "k_desc_normalize"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

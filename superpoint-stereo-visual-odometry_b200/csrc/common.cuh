@@ -24,7 +24,7 @@ struct Handle;
 // (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
 enum KernelId {
   KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
-  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_DESC_PLANES, KID_DESC_NORM, KID_COUNT
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_DESC_PLANES, KID_DESC_NORM, KID_COUNT
 };
 struct ProfRec {
   int kid;
@@ -68,6 +68,8 @@ struct Handle {
   // decode workspace
   float* heat = nullptr;          // [max_batch, max_h*max_w]
   unsigned* hist = nullptr;       // [max_batch, kHistBins]
+  float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)
+  int4* kp_par = nullptr;         // [max_batch, max_k] sampling parameters
   unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)
   // staging for the host-pointer entry points
   float* st_semi = nullptr;

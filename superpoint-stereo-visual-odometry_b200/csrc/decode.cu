@@ -96,6 +96,7 @@ struct DetectParams {
   float* scores;
   int* n_out;
   unsigned long long* counters;
+  int4* kp_par;   // [B,K] sampling parameters for k_desc_planes (may be NULL)
   int cap;        // key buffer capacity (power of two)
   int target;     // candidates wanted in the first chunk
 };
@@ -479,6 +480,23 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
     }
     kp[i] = o;
     if (p.scores) p.scores[(size_t)b * K + i] = sc;
+    if (p.kp_par) {
+      // align-corners sampling coordinates (NN:377-392), same fp32 operation order as the oracle
+      int4 par = make_int4(0, 0, 0, 0);
+      if (i < n_emit) {
+        const float r8 = __fmul_rn(__fdiv_rn(o.y, (float)(H - 1)), (float)(Hc - 1));
+        const float c8 = __fmul_rn(__fdiv_rn(o.x, (float)(W - 1)), (float)(Wc - 1));
+        const int r0 = (int)floorf(r8), c0 = (int)floorf(c8);
+        const float rr = __fsub_rn(1.0f, __fsub_rn(r8, (float)r0));
+        const float cr = __fsub_rn(1.0f, __fsub_rn(c8, (float)c0));
+        const int r1 = min(r0 + 1, Hc - 1), c1 = min(c0 + 1, Wc - 1);
+        par.x = r0 * Wc + c0;
+        par.y = ((r1 - r0) * Wc) | ((c1 - c0) << 30);
+        par.z = __float_as_int(rr);
+        par.w = __float_as_int(cr);
+      }
+      p.kp_par[(size_t)b * K + i] = par;
+    }
   }
   if (tid == 0) {
     p.n_out[b] = n_emit;
@@ -552,6 +570,109 @@ k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3 (streaming form): k_desc_planes + k_desc_normalize.
+// A keypoint touches 4 cells x 256 channels; in NCHW every channel of a cell lives in a different
+// 32-byte sector, so gathering per keypoint moves 2-3x the tensor through L2.  Instead each CTA
+// streams kCP whole channel planes (Hc*Wc floats, contiguous) into shared memory with cp.async --
+// every byte of desc is read exactly once, fully coalesced -- and evaluates the bilinear blend of
+// those channels for ALL keypoints of the image from shared memory.  Values go to a [256][K]
+// scratch (coalesced along K); k_desc_normalize transposes 32 keypoints at a time through shared
+// memory, applies the oracle's norm reduction order and writes the [K][256] rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCP = 2;  // channel planes per CTA: 2 x 29 KB at 1240x376 -> 3 CTAs per SM
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, const int* __restrict__ n_out,
+              float* __restrict__ tmp, int cells, int K, int plane_pitch) {
+  extern __shared__ __align__(16) float sp[];  // kCP planes, each plane_pitch floats
+  const int b = blockIdx.y, cg = blockIdx.x;
+  const int n = n_out[b];
+  if (n == 0) return;
+  int mis[kCP];
+#pragma unroll
+  for (int c = 0; c < kCP; ++c) {
+    const float* src = desc + ((size_t)b * 256 + (size_t)cg * kCP + c) * cells;
+    // keep the 16-byte phase of the global address so the body can use 16-byte cp.async
+    const int m = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    mis[c] = m;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sp + (size_t)c * plane_pitch + m);
+    const int head = min((4 - m) & 3, cells);
+    const int body4 = (cells - head) >> 2;
+    const int tail0 = head + body4 * 4;
+    if (threadIdx.x < head) cp_async4(dst + threadIdx.x * 4, src + threadIdx.x);
+    for (int i = threadIdx.x; i < body4; i += 256) cp_async16(dst + (head + 4 * i) * 4, src + head + 4 * i);
+    if (threadIdx.x < cells - tail0) cp_async4(dst + (tail0 + threadIdx.x) * 4, src + tail0 + threadIdx.x);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int k = threadIdx.x; k < n; k += 256) {
+    const int4 par = kp_par[(size_t)b * K + k];
+    const int o_tl = par.x, dr = par.y & 0x3FFFFFFF, dc = (par.y >> 30) & 1;
+    const float rr = __int_as_float(par.z), cr = __int_as_float(par.w);
+    const float irr = __fsub_rn(1.0f, rr), icr = __fsub_rn(1.0f, cr);
+#pragma unroll
+    for (int c = 0; c < kCP; ++c) {
+      const float* pl = sp + (size_t)c * plane_pitch + mis[c];
+      const float t1 = __fmul_rn(__fmul_rn(pl[o_tl], rr), cr);
+      const float t2 = __fmul_rn(__fmul_rn(pl[o_tl + dc], rr), icr);
+      const float t3 = __fmul_rn(__fmul_rn(pl[o_tl + dr], irr), cr);
+      const float t4 = __fmul_rn(__fmul_rn(pl[o_tl + dr + dc], irr), icr);
+      tmp[((size_t)b * 256 + (size_t)cg * kCP + c) * K + k] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
+    }
+  }
+}
+
+// 32 keypoints per block: [256][K] scratch -> shared [32][257] -> normalised [K][256] rows.
+__global__ void __launch_bounds__(256)
+k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K) {
+  __shared__ float s[32][257];
+  const int b = blockIdx.y, k0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = n_out[b];
+  if (k0 < n) {
+    const float* src = tmp + (size_t)b * 256 * K;
+    if (k0 + lane < n) {
+#pragma unroll 8
+      for (int c = w; c < 256; c += 8) s[lane][c] = __ldg(src + (size_t)c * K + k0 + lane);
+    }
+  }
+  __syncthreads();
+  for (int kk = w; kk < 32; kk += 8) {
+    const int k = k0 + kk;
+    if (k >= K) break;
+    float* o = out + ((size_t)b * K + k) * 256;
+    if (k >= n) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[lane + 32 * i] = 0.0f;
+      continue;
+    }
+    float v[8], part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = s[kk][lane + 32 * i];
+      part = __fadd_rn(part, __fmul_rn(v[i], v[i]));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+    if (part > 0.0f) {
+      const float nrm = __fsqrt_rn(part);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __fdiv_rn(v[i], nrm);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[lane + 32 * i] = v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launcher
 // ------------------------------------------------------------------------------------------------
 static size_t detect_smem_bytes(int H, int W, int K, int cap) {
@@ -578,6 +699,10 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
     p.heat = h->heat; p.hist = h->hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
+    const int plane_pitch = (cells + 4 + 3) & ~3;
+    const size_t smem_planes = (size_t)kCP * plane_pitch * sizeof(float);
+    const bool streaming = desc && desc_out && h->desc_tmp && h->kp_par && smem_planes <= 200 * 1024;
+    p.kp_par = streaming ? h->kp_par : nullptr;
     p.cap = K <= 1536 ? 4096 : 8192;
     p.target = min(p.cap * 3 / 4, K + K / 2 + 256);
     const size_t smem = detect_smem_bytes(H, W, K, p.cap);
@@ -587,7 +712,18 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
       LaunchScope ls(h, KID_DETECT);
       k_detect<<<B, kDetectThreads, smem, st>>>(p);
     }
-    if (desc && desc_out) {
+    if (streaming) {
+      if ((e = cudaFuncSetAttribute(k_desc_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
+        return e;
+      {
+        LaunchScope ls(h, KID_DESC_PLANES);
+        k_desc_planes<<<dim3(256 / kCP, B), 256, smem_planes, st>>>(desc, h->kp_par, n_out, h->desc_tmp, cells, K, plane_pitch);
+      }
+      {
+        LaunchScope ls(h, KID_DESC_NORM);
+        k_desc_normalize<<<dim3((K + 31) / 32, B), 256, 0, st>>>(h->desc_tmp, n_out, desc_out, K);
+      }
+    } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);
       LaunchScope ls(h, KID_SAMPLE_DESC);
       k_sample_desc<<<g3, 256, 0, st>>>(desc, kpts, n_out, desc_out, H, W, K);

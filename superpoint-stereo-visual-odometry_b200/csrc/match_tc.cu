@@ -426,6 +426,11 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
         atomicAdd(&counters[1], 1ull);
       }
       return;
+    } else if (nc == 1 && !knn) {
+      // the nearest neighbour is proved without evaluating any distance; DMatch.distance is filled in
+      // by k_tc_fill_dist only for the matches that survive (marker: negative distance)
+      x0 = jx[0];
+      b0 = -1.0f;
     } else {
       for (int c = half; c < nc + half; c += 2) {
         const int cc = c < nc ? c : nc - 1;
@@ -454,6 +459,30 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
     }
   }
+}
+
+// k_tc_fill_dist: exact DMatch.distance for the forward matches whose index was proved without a
+// distance (row_d < 0) and that survive the cross-check.  Half a warp per query row.
+__global__ void __launch_bounds__(256)
+k_tc_fill_dist(const MatchProblem* __restrict__ probs, int mode, int max_rows, int max_cols,
+               const int* __restrict__ row_best, float* __restrict__ row_d, const int* __restrict__ col_best) {
+  const int p = blockIdx.y;
+  const MatchProblem pr = probs[p];
+  const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int i = blockIdx.x * 16 + (threadIdx.x >> 5) * 2 + half;
+  if (blockIdx.x * 16 >= pr.N) return;
+  bool need = false;
+  int j = 0;
+  const size_t o = ((size_t)p * max_rows + (i < pr.N ? i : 0)) * 2;
+  if (i < pr.N && pr.M > 0) {
+    j = row_best[o];
+    need = j >= 0 && row_d[o] < 0.0f;
+    if (need && mode == SPVO_MATCH_NN_CROSSCHECK) need = col_best[(size_t)p * max_cols + j] == i;
+  }
+  if (!__any_sync(0xffffffffu, need)) return;
+  const int ii = need ? i : 0, jj = need ? j : 0;
+  const float d = exact_dist_half(pr.q + (size_t)ii * kDim, pr.t + (size_t)jj * kDim, l16);
+  if (need && l16 == 0) row_d[o] = d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -502,42 +531,54 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
     }
     float v[3] = {INFINITY, INFINITY, INFINITY};
     int ix[3] = {-1, -1, -1};
-    for (int j = warp; j < Nb; j += 8) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
-      const float4 y = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
-      const float b[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-      float pd[kFbRows];
+    constexpr int kU = 4;  // columns in flight per warp
+    for (int jb = warp; jb < Nb; jb += 8 * kU) {
+      float4 xs[kU], ys[kU];
 #pragma unroll
-      for (int r = 0; r < kFbRows; ++r) {
-        float t = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t = __fmaf_rn(a[r][e], b[e], t);
-        pd[r] = t;
-      }
-      // reduce 8 values over 32 lanes: halve the value set at xor 16 / 8 / 4, then finish at xor 2 / 1
-      float q4[4], q2[2], q1;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float keep = (lane & 16) ? pd[r + 4] : pd[r], send = (lane & 16) ? pd[r] : pd[r + 4];
-        q4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      for (int u = 0; u < kU; ++u) {
+        const int j = min(jb + 8 * u, Nb - 1);
+        xs[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
+        ys[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
       }
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float keep = (lane & 8) ? q4[r + 2] : q4[r], send = (lane & 8) ? q4[r] : q4[r + 2];
-        q2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-      {
-        const float keep = (lane & 4) ? q2[1] : q2[0], send = (lane & 4) ? q2[0] : q2[1];
-        q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-      q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-      const float g = __fmaf_rn(-2.0f, q1, nbv[j]);
-      if (g < v[2]) {
-        if (g < v[1]) {
-          v[2] = v[1]; ix[2] = ix[1];
-          if (g < v[0]) { v[1] = v[0]; ix[1] = ix[0]; v[0] = g; ix[0] = j; } else { v[1] = g; ix[1] = j; }
-        } else { v[2] = g; ix[2] = j; }
+      for (int u = 0; u < kU; ++u) {
+        const int j = jb + 8 * u;
+        const float b[8] = {xs[u].x, xs[u].y, xs[u].z, xs[u].w, ys[u].x, ys[u].y, ys[u].z, ys[u].w};
+        float pd[kFbRows];
+#pragma unroll
+        for (int r = 0; r < kFbRows; ++r) {
+          float t = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t = __fmaf_rn(a[r][e], b[e], t);
+          pd[r] = t;
+        }
+        // reduce 8 values over 32 lanes: halve the value set at xor 16 / 8 / 4, then finish at xor 2 / 1
+        float q4[4], q2[2], q1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float keep = (lane & 16) ? pd[r + 4] : pd[r], send = (lane & 16) ? pd[r] : pd[r + 4];
+          q4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float keep = (lane & 8) ? q4[r + 2] : q4[r], send = (lane & 8) ? q4[r] : q4[r + 2];
+          q2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+          const float keep = (lane & 4) ? q2[1] : q2[0], send = (lane & 4) ? q2[0] : q2[1];
+          q1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+        if (j < Nb) {
+          const float g = __fmaf_rn(-2.0f, q1, nbv[j]);
+          if (g < v[2]) {
+            if (g < v[1]) {
+              v[2] = v[1]; ix[2] = ix[1];
+              if (g < v[0]) { v[1] = v[0]; ix[1] = ix[0]; v[0] = g; ix[0] = j; } else { v[1] = g; ix[1] = j; }
+            } else { v[2] = g; ix[2] = j; }
+          }
+        }
       }
     }
     if ((lane & 3) == 0) {
@@ -736,6 +777,11 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       LaunchScope ls(h, KID_TC_FALLBACK);
       k_tc_fallback<<<ndir, 256, 0, st>>>(probs, P, cfg.mode, w->nrm, cap, mr, mc, w->fb_count, w->fb_list,
                                           h->row_best, h->row_d, h->col_best, h->counters);
+    }
+    if (cfg.mode != SPVO_MATCH_KNN_RATIO) {
+      LaunchScope ls(h, KID_TC_FILL);
+      k_tc_fill_dist<<<dim3((max_rows + 15) / 16, P), 256, 0, st>>>(probs, cfg.mode, mr, mc, h->row_best, h->row_d,
+                                                                   h->col_best);
     }
   }
   return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
