@@ -221,15 +221,21 @@ static int check_match_cfg(Handle* h, const spvo_match_cfg* cfg, int dim) {
   return SPVO_OK;
 }
 
-static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
-                     const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride) {
+static int pick_algorithm(const spvo_match_cfg* cfg, int max_rows, int max_cols) {
   // AUTO: the tensor-core path unless the problems are too small to fill a 128 x 128 tile.
   int alg = cfg->algorithm;
   if (alg == SPVO_MATCHER_AUTO)
     alg = ((long long)max_rows * max_cols >= 128 * 128) ? SPVO_MATCHER_TENSOR : SPVO_MATCHER_EXACT_FP32;
   if (max_rows > 8192 || max_cols > 8192) alg = SPVO_MATCHER_EXACT_FP32;  // packed shortlist keys carry 13 index bits
+  return alg;
+}
+
+static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
+                     const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride,
+                     bool operands_ready = false) {
+  const int alg = pick_algorithm(cfg, max_rows, max_cols);
   if (alg == SPVO_MATCHER_TENSOR)
-    CK(launch_match_tc(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
+    CK(launch_match_tc(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride, operands_ready));
   else
     CK(launch_match_exact(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride));
   return SPVO_OK;
@@ -366,7 +372,13 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   cudaStream_t st = h->stream;
   int rc = ensure_carry(h);
   if (rc) return rc;
-  CK(launch_decode(h, semi, desc, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr));
+  // tensor matcher: decode writes each image's bf16 operand straight into slot = image index;
+  // slot max_batch holds the carried last-left image of the previous batch
+  const bool tensor = pick_algorithm(&cfg->match, K, K) == SPVO_MATCHER_TENSOR;
+  const int carry_slot = h->max_batch;
+  TcSink sink;
+  if (tensor) CK(tc_prepare_slots(h, h->max_batch + 1, h->max_k, 2 * h->max_batch, &sink));
+  CK(launch_decode(h, semi, desc, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr, tensor ? &sink : nullptr));
   if (2 * F > h->probs_cap) {
     cudaFree(h->probs);
     h->probs = nullptr;
@@ -374,8 +386,11 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
     CK(cudaMalloc((void**)&h->probs, (size_t)2 * F * sizeof(MatchProblem)));
     h->probs_cap = 2 * F;
   }
-  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K));
-  rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K);
+  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot));
+  if (tensor && h->has_prev && !h->carry_tc_valid)
+    // the previous batch ran on the exact matcher: convert the carried fp32 descriptors into the carry slot
+    CK(tc_prep_problem_operands(h, h->probs + F));
+  rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K, tensor);
   if (rc) return rc;
   if (keep)
     CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
@@ -385,6 +400,8 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   CK(cudaMemcpyAsync(h->carry_desc, desc_out + last * K * 256, (size_t)K * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->carry_kpts, kpts + last * K, (size_t)K * sizeof(spvo_keypoint), cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->carry_n, n_kpts + last, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (tensor) CK(tc_copy_slot(h, carry_slot, (int)last));
+  h->carry_tc_valid = tensor;
   h->has_prev = true;
   return SPVO_OK;
 }

@@ -36,23 +36,38 @@ struct MatchProblem {
   const float* q;  // [N,256]
   const float* t;  // [M,256]
   int N, M;
+  int a_op, b_op;  // operand slots of q / t in the tensor matcher's bf16 workspace (match_tc.cu)
+};
+
+// Where k_desc_normalize additionally writes each image's descriptors for the tensor matcher
+// (bf16 rows + fp32 squared norms + per-slot max norm), so the stereo pipeline needs no k_tc_prep.
+struct TcSink {
+  void* xb = nullptr;        // __nv_bfloat16 [slots][cap][256]
+  float* nrm = nullptr;      // [slots][cap]
+  unsigned* opmax = nullptr; // [slots]
+  int cap = 0;               // rows per slot (multiple of 128)
 };
 
 // ---- decode.cu ----
 cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                          float* scores);
+                          float* scores, const TcSink* sink = nullptr);
 // ---- match.cu ----
 cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                                const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
                                int out_stride);
 cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
-                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride);
+                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride,
+                            bool operands_ready = false);
+// Stereo pipeline: reserve max_batch image slots + 1 carry slot and return where decode should write.
+cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink);
+cudaError_t tc_copy_slot(Handle* h, int dst_slot, int src_slot);
+cudaError_t tc_prep_problem_operands(Handle* h, const MatchProblem* prob);  // k_tc_prep for one problem's q and t
 void tc_workspace_free(Handle* h);
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
-                                         int F, int K);
+                                         int F, int K, int carry_slot);
 cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
 cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                  const int* q_slot, const int* t_slot, int P, int max_rows,
@@ -98,6 +113,7 @@ struct Handle {
   spvo_keypoint* carry_kpts = nullptr;
   int* carry_n = nullptr;           // device int; 0 when there is no previous frame
   bool has_prev = false;
+  bool carry_tc_valid = false;      // the carry's bf16 copy exists in the tensor matcher's carry slot
   // host-form staging of the stereo outputs
   spvo_dmatch* st_smatches = nullptr;
   int* st_snm = nullptr;

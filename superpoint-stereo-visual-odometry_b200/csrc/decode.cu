@@ -12,6 +12,8 @@
 //
 // HBM-bound integer/float streaming work: coalesced 128 B channel-plane reads of semi, 32 B-aligned
 // float4 heatmap stores, warp-shuffle reductions; no tensor cores here.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace spvo {
@@ -632,7 +634,8 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
 
 // 32 keypoints per block: [256][K] scratch -> shared [32][257] -> normalised [K][256] rows.
 __global__ void __launch_bounds__(256)
-k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K) {
+k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K,
+                 TcSink sink) {
   __shared__ float s[32][257];
   const int b = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -645,9 +648,17 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
     }
   }
   __syncthreads();
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(sink.xb);
+  float smax = 0.f;
   for (int kk = w; kk < 32; kk += 8) {
     const int k = k0 + kk;
-    if (k >= K) break;
+    if (xb && k < sink.cap && k >= n) {  // padded rows of the matcher slot: zero row, norm = +inf
+      const size_t row = (size_t)b * sink.cap + k;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xb[row * 256 + lane + 32 * i] = __float2bfloat16_rn(0.0f);
+      if (lane == 0) sink.nrm[row] = INFINITY;
+    }
+    if (k >= K) continue;
     float* o = out + ((size_t)b * K + k) * 256;
     if (k >= n) {
 #pragma unroll
@@ -669,7 +680,21 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[lane + 32 * i] = v[i];
+    if (xb) {  // tensor-matcher operand: bf16 row + squared norm of the fp32 row (any summation order)
+      const size_t row = (size_t)b * sink.cap + k;
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xb[row * 256 + lane + 32 * i] = __float2bfloat16_rn(v[i]);
+        s2 = __fmaf_rn(v[i], v[i], s2);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+      if (lane == 0) sink.nrm[row] = s2;
+      smax = fmaxf(smax, s2);
+    }
   }
+  if (xb && lane == 0 && smax > 0.f) atomicMax(&sink.opmax[b], __float_as_uint(smax));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -683,7 +708,7 @@ static size_t detect_smem_bytes(int H, int W, int K, int cap) {
 
 cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                          float* scores) {
+                          float* scores, const TcSink* sink) {
   cudaStream_t st = h->stream;
   const int Hc = H / 8, Wc = W / 8, cells = Hc * Wc, K = cfg.max_keypoints;
   cudaError_t e;
@@ -721,7 +746,13 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
       }
       {
         LaunchScope ls(h, KID_DESC_NORM);
-        k_desc_normalize<<<dim3((K + 31) / 32, B), 256, 0, st>>>(h->desc_tmp, n_out, desc_out, K);
+        TcSink sk;
+        if (sink) {
+          sk = *sink;
+          if ((e = cudaMemsetAsync(sk.opmax, 0, (size_t)B * sizeof(unsigned), st)) != cudaSuccess) return e;
+        }
+        const int rows = sk.xb ? sk.cap : K;
+        k_desc_normalize<<<dim3((rows + 31) / 32, B), 256, 0, st>>>(h->desc_tmp, n_out, desc_out, K, sk);
       }
     } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);

@@ -228,13 +228,15 @@ __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, co
   pr.t = desc_base + (size_t)ts * slot_stride_rows * kD;
   pr.N = n_rows[qs];
   pr.M = n_rows[ts];
+  pr.a_op = 2 * p;
+  pr.b_op = 2 * p + 1;
   probs[p] = pr;
 }
 
 // Stereo stream problems: p < F stereo (left_f vs right_f); p >= F temporal (left_f vs left_{f-1},
 // or the carried last-left of the previous batch for f = 0; carry_n = 0 means "no previous frame").
 __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_out, const int* n_out,
-                                        const float* carry_desc, const int* carry_n, int F, int K) {
+                                        const float* carry_desc, const int* carry_n, int F, int K, int carry_slot) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= 2 * F) return;
   MatchProblem pr;
@@ -243,16 +245,21 @@ __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_o
     pr.t = desc_out + (size_t)(2 * p + 1) * K * kD;
     pr.N = n_out[2 * p];
     pr.M = n_out[2 * p + 1];
+    pr.a_op = 2 * p;       // operand slot = image index (bf16 rows written by k_desc_normalize)
+    pr.b_op = 2 * p + 1;
   } else {
     const int f = p - F;
     pr.q = desc_out + (size_t)(2 * f) * K * kD;
     pr.N = n_out[2 * f];
+    pr.a_op = 2 * f;
     if (f > 0) {
       pr.t = desc_out + (size_t)(2 * (f - 1)) * K * kD;
       pr.M = n_out[2 * (f - 1)];
+      pr.b_op = 2 * (f - 1);
     } else {
       pr.t = carry_desc;
       pr.M = *carry_n;
+      pr.b_op = carry_slot;
     }
   }
   probs[p] = pr;
@@ -261,6 +268,7 @@ __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_o
 __global__ void k_set_problem(MatchProblem* probs, const float* q, int N, const float* t, int M) {
   MatchProblem pr;
   pr.q = q; pr.t = t; pr.N = N; pr.M = M;
+  pr.a_op = 0; pr.b_op = 1;
   probs[0] = pr;
 }
 
@@ -362,12 +370,12 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
 }
 
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
-                                         int F, int K) {
+                                         int F, int K, int carry_slot) {
   if (F == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
     k_setup_stereo_problems<<<(2 * F + 127) / 128, 128, 0, h->stream>>>(probs, desc_out, n_out, h->carry_desc,
-                                                                       h->carry_n, F, K);
+                                                                       h->carry_n, F, K, carry_slot);
   }
   return cudaGetLastError();
 }

@@ -135,29 +135,41 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
   const MatchProblem pr = probs[p];
   const float* src = (o & 1) ? pr.t : pr.q;
   const int n = (o & 1) ? pr.M : pr.N;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= cap) return;
-  const size_t row = (size_t)o * cap + r;
-  uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-  float s = 0.0f;
-  if (r < n) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kDim) + 2 * lane);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kDim) + 2 * lane + 1);
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+  const int slot = (o & 1) ? pr.b_op : pr.a_op;
+  const int lane = threadIdx.x & 31;
+  const int rbase = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;  // 4 rows per warp: 8 loads in flight per lane
+  if (rbase >= cap) return;
+  float4 a[4], b[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rbase + u < n) {
+      a[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(rbase + u) * kDim) + 2 * lane);
+      b[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(rbase + u) * kDim) + 2 * lane + 1);
+    }
+  }
+  float smax = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = rbase + u;
+    if (r >= cap) break;
+    const size_t row = (size_t)slot * cap + r;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a[u].x, a[u].y), h1 = __floats2bfloat162_rn(a[u].z, a[u].w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b[u].x, b[u].y), h3 = __floats2bfloat162_rn(b[u].z, b[u].w);
+    uint4 packed;
     packed.x = *reinterpret_cast<uint32_t*>(&h0);
     packed.y = *reinterpret_cast<uint32_t*>(&h1);
     packed.z = *reinterpret_cast<uint32_t*>(&h2);
     packed.w = *reinterpret_cast<uint32_t*>(&h3);
-    s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-  }
+    float s = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w + b[u].x * b[u].x +
+              b[u].y * b[u].y + b[u].z * b[u].z + b[u].w * b[u].w;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  reinterpret_cast<uint4*>(xb + row * kDim)[lane] = packed;
-  if (lane == 0) {
-    nrm[row] = r < n ? s : INFINITY;
-    if (r < n) atomicMax(&opmax[o], __float_as_uint(s));
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    reinterpret_cast<uint4*>(xb + row * kDim)[lane] = packed;
+    if (lane == 0) nrm[row] = r < n ? s : INFINITY;
+    if (r < n) smax = fmaxf(smax, s);
   }
+  if (lane == 0 && smax > 0.f) atomicMax(&opmax[slot], __float_as_uint(smax));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,7 +207,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
   const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
-  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
   const int rb = blockIdx.x;
   if (rb * kBM >= Na) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
   const int nct = (Nb + kBN - 1) / kBN;
@@ -357,7 +369,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
   const float* A = rev ? pr.t : pr.q;
   const float* B = rev ? pr.q : pr.t;
-  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   if (i >= Na) return;
   float b0 = INFINITY, b1 = INFINITY;
@@ -511,7 +523,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
   const int Nb = rev ? pr.N : pr.M;
   const float* A = rev ? pr.t : pr.q;
   const float* B = rev ? pr.q : pr.t;
-  const int a_op = rev ? 2 * p + 1 : 2 * p, b_op = rev ? 2 * p : 2 * p + 1;
+  const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
   const float* nbv = nrm + (size_t)b_op * cap;
   const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
@@ -686,6 +698,7 @@ struct TcWorkspace {
   int* fb_count = nullptr;
   int* fb_list = nullptr;
   size_t rows = 0, ops = 0, top_rows = 0;
+  int slot_cap = 0;  // rows per operand slot of the current layout
   CUtensorMap tmap;
 };
 
@@ -740,27 +753,72 @@ cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, in
                                  const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride);
 cudaError_t ensure_select_buffers(Handle* h, int P, int mr, int mc);
 
+static cudaError_t tc_get(Handle* h, TcWorkspace** w, size_t ops, size_t cap, size_t ndir) {
+  if (!h->tc_ws) h->tc_ws = new TcWorkspace();
+  *w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+  return tc_ensure(h, *w, ops, cap, ndir);
+}
+
+cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink) {
+  TcWorkspace* w;
+  const int cap = (max_rows + kBM - 1) / kBM * kBM;
+  cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir);
+  if (e != cudaSuccess) return e;
+  w->slot_cap = cap;
+  sink->xb = w->xb;
+  sink->nrm = w->nrm;
+  sink->opmax = w->opmax;
+  sink->cap = cap;
+  return cudaSuccess;
+}
+
+cudaError_t tc_copy_slot(Handle* h, int dst, int src) {
+  TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+  if (!w) return cudaErrorInvalidValue;
+  const size_t cap = w->slot_cap;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(w->xb + (size_t)dst * cap * kDim, w->xb + (size_t)src * cap * kDim,
+                           cap * kDim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, h->stream)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(w->nrm + (size_t)dst * cap, w->nrm + (size_t)src * cap, cap * sizeof(float),
+                           cudaMemcpyDeviceToDevice, h->stream)) != cudaSuccess) return e;
+  return cudaMemcpyAsync(w->opmax + dst, w->opmax + src, sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream);
+}
+
+cudaError_t tc_prep_problem_operands(Handle* h, const MatchProblem* prob) {
+  TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+  if (!w || !w->slot_cap) return cudaErrorInvalidValue;
+  LaunchScope ls(h, KID_TC_PREP);
+  k_tc_prep<<<dim3((w->slot_cap + 31) / 32, 2), 256, 0, h->stream>>>(prob, w->xb, w->nrm, w->opmax, w->slot_cap);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
-                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride) {
+                            const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride,
+                            bool operands_ready) {
   cudaStream_t st = h->stream;
   cudaError_t e;
   if (P == 0) return cudaSuccess;
   const int mr = max_rows > 0 ? max_rows : 1, mc = max_cols > 0 ? max_cols : 1;
   if ((e = ensure_select_buffers(h, P, mr, mc)) != cudaSuccess) return e;
   if (max_rows > 0 && max_cols > 0) {
-    if (!h->tc_ws) h->tc_ws = new TcWorkspace();
-    TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
     const int mx = max_rows > max_cols ? max_rows : max_cols;
-    const int cap = (mx + kBM - 1) / kBM * kBM;
+    int cap = (mx + kBM - 1) / kBM * kBM;
     const bool cross = cfg.mode == SPVO_MATCH_NN_CROSSCHECK;
     const int ndir = cross ? 2 * P : P;
-    if ((e = tc_ensure(h, w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
-    {
+    TcWorkspace* w;
+    if (operands_ready) {
+      // the stereo pipeline already reserved the slots and k_desc_normalize filled them
+      w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
+      if (!w || w->top_rows < (size_t)ndir * w->slot_cap) return cudaErrorInvalidValue;
+      cap = w->slot_cap;
+    } else {
+      if ((e = tc_get(h, &w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
+      w->slot_cap = cap;
+      if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
       LaunchScope ls(h, KID_TC_PREP);
-      k_tc_prep<<<dim3(cap / 8, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap);
+      k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap);
     }
+    if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
     const size_t smem = 1024 + (size_t)(1 + kStages) * kNumKB * kTileBytes + sizeof(TcShared);
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
@@ -770,8 +828,8 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     {
       LaunchScope ls(h, KID_TC_RERANK);
       k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
-                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count, w->fb_list,
-                                                     h->counters);
+                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count,
+                                                     w->fb_list, h->counters);
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);

@@ -80,3 +80,20 @@ def test_stereo_batch_host_and_device(spvo, oracle, mode):
         torch.cuda.synchronize()
         _check_batch(S, {k: v.cpu().numpy() for k, v in dout.items()}, ref, b * F, F, K)
     fe.close()
+
+
+def test_stereo_batch_algorithm_switch_keeps_the_carry(spvo, oracle):
+    """Consecutive batches on different matcher algorithms (exact fp32 <-> tensor) continue one sequence."""
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, F = 192, 640, 500, 2
+    semi, desc = synth.make_stream(3 * F, H, W, seed=8, device="cpu")
+    semi, desc = semi.numpy(), desc.numpy()
+    ref = _oracle_stream(oracle, semi, desc, K, 1, 2.0, 0.25)
+    fe = S.Frontend(0, 2 * F, H, W, K)
+    for b, alg in enumerate((S.MATCHER_EXACT_FP32, S.MATCHER_TENSOR, S.MATCHER_TENSOR)):
+        out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
+        fe.stereo_batch(semi[b * F:(b + 1) * F], desc[b * F:(b + 1) * F], F, H, W, out, max_keypoints=K, mode=1,
+                        algorithm=alg)
+        _check_batch(S, out, ref, b * F, F, K)
+    fe.close()
