@@ -42,7 +42,8 @@ struct MatchProblem {
 // Where k_desc_normalize additionally writes each image's descriptors for the tensor matcher
 // (bf16 rows + fp32 squared norms + per-slot max norm), so the stereo pipeline needs no k_tc_prep.
 struct TcSink {
-  void* xb = nullptr;        // __nv_bfloat16 [slots][cap][256]
+  void* xb = nullptr;        // 16-bit operands [slots][cap][256]: fp16 when fp16 != 0, else bf16
+  int fp16 = 0;
   float* nrm = nullptr;      // [slots][cap]
   unsigned* opmax = nullptr; // [slots]
   int cap = 0;               // rows per slot (multiple of 128)

@@ -13,6 +13,7 @@
 // HBM-bound integer/float streaming work: coalesced 128 B channel-plane reads of semi, 32 B-aligned
 // float4 heatmap stores, warp-shuffle reductions; no tensor cores here.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -648,14 +649,14 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
     }
   }
   __syncthreads();
-  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(sink.xb);
+  unsigned short* xb = reinterpret_cast<unsigned short*>(sink.xb);
   float smax = 0.f;
   for (int kk = w; kk < 32; kk += 8) {
     const int k = k0 + kk;
     if (xb && k < sink.cap && k >= n) {  // padded rows of the matcher slot: zero row, norm = +inf
       const size_t row = (size_t)b * sink.cap + k;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xb[row * 256 + lane + 32 * i] = __float2bfloat16_rn(0.0f);
+      for (int i = 0; i < 8; ++i) xb[row * 256 + lane + 32 * i] = 0;
       if (lane == 0) sink.nrm[row] = INFINITY;
     }
     if (k >= K) continue;
@@ -685,7 +686,8 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
       float s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        xb[row * 256 + lane + 32 * i] = __float2bfloat16_rn(v[i]);
+        xb[row * 256 + lane + 32 * i] = sink.fp16 ? __half_as_ushort(__float2half_rn(v[i]))
+                                                  : __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
         s2 = __fmaf_rn(v[i], v[i], s2);
       }
 #pragma unroll

@@ -28,6 +28,7 @@
 // (B against A) in the same launch; D(a,b) is bitwise symmetric in OpenCV's arithmetic.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <limits.h>
 
 #include "common.cuh"
@@ -44,10 +45,14 @@ constexpr int kTop = 3;
 constexpr int kEpiWarps = 8;              // 2 per TMEM lane quadrant: each owns 64 of a tile's 128 columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int kLists = 2;                 // shortlists per row (one per column half), merged by k_tc_rerank
-constexpr float kEpsRel = 0.0085f, kEpsAbs = 1e-5f;
-constexpr int kIdxBits = 13;              // packed key = (bits(g + off) & ~0x1FFF) | column  (columns < 8192)
-constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
-constexpr float kKeyRel = 1.0f / 1024.0f; // truncating 13 mantissa bits loses < 2^-10 of the (positive) value
+// |approx d^2 - exact d^2| <= eps_rel*|a||b| + kEpsAbs*(|a|^2+|b|^2):
+//   bf16 operands (any CV_32F input):        2*(2^-8  + 2^-18 + 2^-14) -> 0.0085
+//   fp16 operands (|x| <= 1, unit-norm rows): 2*(2^-10 + 2^-22 + 2^-14) -> 0.0022; fp16 subnormals (|x| < 2^-14) add
+//   <= 2*256*2^-25 per unit of max|b_k| -> covered by kEpsAbs.
+constexpr float kEpsRelBf16 = 0.0085f, kEpsRelFp16 = 0.0022f, kEpsAbs = 1e-5f;
+// packed key = (bits(g + off) & ~mask) | column, mask = 2^idx_bits - 1 with 2^idx_bits >= rows per slot;
+// truncating idx_bits mantissa bits loses < 2^(idx_bits-23) of the (positive) value
+constexpr int kMaxIdxBits = 13;
 
 // Offset that makes every g_ij + off positive, so fp32 bit patterns order like the values:
 // g = |b|^2 - 2 a.b >= -2|a||b| >= -2 sqrt(amax2 * bmax2).
@@ -87,6 +92,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -122,7 +132,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
          (2ull << 61);
 }
 // Instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128 (>>3), M = 128 (>>4).
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// a_format / b_format: 0 = F16, 1 = BF16.
+__host__ __device__ constexpr uint32_t make_idesc(bool fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(kBN >> 3) << 17) |
+         ((uint32_t)(kBM >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_tc_prep: operand o = 2p (query of problem p) or 2p+1 (train).  One warp per workspace row.
@@ -130,7 +144,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb, float* __restrict__ nrm,
-          unsigned* __restrict__ opmax, int cap) {
+          unsigned* __restrict__ opmax, int cap, int fp16) {
   const int o = blockIdx.y, p = o >> 1;
   const MatchProblem pr = probs[p];
   const float* src = (o & 1) ? pr.t : pr.q;
@@ -161,6 +175,14 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
     packed.y = *reinterpret_cast<uint32_t*>(&h1);
     packed.z = *reinterpret_cast<uint32_t*>(&h2);
     packed.w = *reinterpret_cast<uint32_t*>(&h3);
+    if (fp16) {
+      __half2 f0 = __floats2half2_rn(a[u].x, a[u].y), f1 = __floats2half2_rn(a[u].z, a[u].w);
+      __half2 f2 = __floats2half2_rn(b[u].x, b[u].y), f3 = __floats2half2_rn(b[u].z, b[u].w);
+      packed.x = *reinterpret_cast<uint32_t*>(&f0);
+      packed.y = *reinterpret_cast<uint32_t*>(&f1);
+      packed.z = *reinterpret_cast<uint32_t*>(&f2);
+      packed.w = *reinterpret_cast<uint32_t*>(&f3);
+    }
     float s = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w + b[u].x * b[u].x +
               b[u].y * b[u].y + b[u].z * b[u].z + b[u].w * b[u].w;
 #pragma unroll
@@ -175,7 +197,9 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 // ------------------------------------------------------------------------------------------------
 // k_tc_gemm
 // ------------------------------------------------------------------------------------------------
-struct __align__(8) TcShared {
+constexpr int kNormRing = 4;  // tile ct's column norms live in slot ct % 4 (see the producer for why 4 is safe)
+struct __align__(16) TcShared {
+  float nrm[kNormRing][kBN];
   uint64_t a_full;
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t acc_full[kStages], acc_empty[kStages];
@@ -201,7 +225,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs, int P,
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
-          int cap) {
+          int cap, uint32_t idesc, uint32_t idx_mask) {
   extern __shared__ uint8_t smem_raw[];
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
@@ -249,10 +273,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
       for (int ct = 0; ct < nct; ++ct) {
         const int s = ct % kStages, ph = (ct / kStages) & 1;
         mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
-        mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes);
+        mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes + kBN * 4);
         const int b_row = b_op * cap + ct * kBN;
         for (int kb = 0; kb < kNumKB; ++kb)
           tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
+        // the tile's 128 column norms ride on the same barrier.  Slot ct % 4 is rewritten by tile ct+4, whose
+        // load waits for the MMAs of tile ct+2, which waited for the epilogue to drain tile ct: no race.
+        bulk_load_1d(smem_u32(&sh->nrm[ct % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, smem_u32(&sh->b_full[s]));
       }
     }
   } else if (warp == 1) {
@@ -271,7 +298,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           for (int k = 0; k < kKB / 16; ++k) {
             const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
             const uint64_t bd = umma_desc_sw128(sB + (s * kNumKB + kb) * kTileBytes + k * 32);
-            tc_mma_bf16(d, ad, bd, kIdesc, (kb | k) != 0);
+            tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
           }
         }
         tc_commit(smem_u32(&sh->b_empty[s]));   // smem stage free once these MMAs retire
@@ -283,19 +310,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = rb * kBM + quad * 32 + lane;
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    const float* nb = nrm + (size_t)b_op * cap;
     const float off = key_offset(__uint_as_float(opmax[a_op]), __uint_as_float(opmax[b_op]));
     for (int ct = 0; ct < nct; ++ct) {
       const int s = ct % kStages, ph = (ct / kStages) & 1;
       const int j0 = ct * kBN + half * 64;
-      // the 64 column norms do not depend on the MMA: fetch them before waiting for the accumulator
-      float4 n4[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) n4[e] = __ldg(reinterpret_cast<const float4*>(nb + j0) + e);
       mbar_wait(smem_u32(&sh->acc_full[s]), ph);
       tc_fence_after();
       uint32_t acc[64];
       tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
+      // the tile's column norms were bulk-copied to shared memory with its B operand (broadcast LDS.128)
+      float4 n4[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[ct % kNormRing][half * 64 + 4 * e]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
@@ -306,7 +332,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         for (int u = 0; u < 4; ++u) {
           // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
           const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
-          const uint32_t key = (__float_as_uint(g) & ~kIdxMask) | (uint32_t)(j0 + 4 * e + u);
+          const uint32_t key = (__float_as_uint(g) & ~idx_mask) | (uint32_t)(j0 + 4 * e + u);
           top3_net(key, k0, k1, k2);
         }
       }
@@ -362,7 +388,8 @@ __global__ void __launch_bounds__(256)
 k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
             const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
             int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
-            int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters) {
+            int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
+            float eps_rel, uint32_t idx_mask, float key_rel) {
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -390,14 +417,14 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
     int jx[kTop];
 #pragma unroll
     for (int k = 0; k < kTop; ++k) {
-      g[k] = __uint_as_float(kk[k] & ~kIdxMask) - off;   // truncated: true value in [g, g + kKeyRel*(g+off))
-      jx[k] = (int)(kk[k] & kIdxMask);
+      g[k] = __uint_as_float(kk[k] & ~idx_mask) - off;   // truncated: true value in [g, g + key_rel*(g+off))
+      jx[k] = (int)(kk[k] & idx_mask);
     }
     // bound on |approx - exact| of any relevant column of this row, plus the key truncation
-    const float eps = kEpsRel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
+    const float eps = eps_rel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
     const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
     const float ref = knn ? g[1] : g[0];
-    const float slack = 2.0f * eps + kKeyRel * (ref + 2.0f * eps + off) * 1.01f;
+    const float slack = 2.0f * eps + key_rel * (ref + 2.0f * eps + off) * 1.01f;
     int nc;
     if (Nb <= kTop) {
       nc = Nb;  // the shortlist is the whole row
@@ -410,11 +437,11 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       while (nc < kTop && g[nc] <= g[1] + slack) ++nc;
       if (nc == kTop) {
         // exact second best unknown; the ratio decision may still be provable from the bound
-        const float slack0 = 2.0f * eps + kKeyRel * (g[0] + 2.0f * eps + off) * 1.01f;
+        const float slack0 = 2.0f * eps + key_rel * (g[0] + 2.0f * eps + off) * 1.01f;
         if (g[1] > g[0] + slack0) {
           const float d0 = exact_dist_half(arow, B + (size_t)jx[0] * kDim, l16);
           const float lo2 = g[1] + na - eps;                                     // exact second best d^2 >= lo2
-          const float hi2 = g[1] + na + eps + kKeyRel * (g[1] + off) * 1.01f;    // and <= hi2
+          const float hi2 = g[1] + na + eps + key_rel * (g[1] + off) * 1.01f;    // and <= hi2
           const float lo = sqrtf(fmaxf(lo2, 0.0f)) * (1.0f - 1e-6f);
           const float hi = sqrtf(fmaxf(hi2, 0.0f)) * (1.0f + 1e-6f);
           if (d0 < ratio * lo) {  // passes for any admissible second best
@@ -699,6 +726,7 @@ struct TcWorkspace {
   int* fb_list = nullptr;
   size_t rows = 0, ops = 0, top_rows = 0;
   int slot_cap = 0;  // rows per operand slot of the current layout
+  bool fp16 = false; // operand format of the current contents (false: bf16)
   CUtensorMap tmap;
 };
 
@@ -765,6 +793,8 @@ cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSin
   cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir);
   if (e != cudaSuccess) return e;
   w->slot_cap = cap;
+  w->fp16 = true;  // decode's descriptors are unit-norm (NN:428): fp16 is range-safe and 8x finer than bf16
+  sink->fp16 = 1;
   sink->xb = w->xb;
   sink->nrm = w->nrm;
   sink->opmax = w->opmax;
@@ -788,7 +818,7 @@ cudaError_t tc_prep_problem_operands(Handle* h, const MatchProblem* prob) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
   if (!w || !w->slot_cap) return cudaErrorInvalidValue;
   LaunchScope ls(h, KID_TC_PREP);
-  k_tc_prep<<<dim3((w->slot_cap + 31) / 32, 2), 256, 0, h->stream>>>(prob, w->xb, w->nrm, w->opmax, w->slot_cap);
+  k_tc_prep<<<dim3((w->slot_cap + 31) / 32, 2), 256, 0, h->stream>>>(prob, w->xb, w->nrm, w->opmax, w->slot_cap, w->fp16 ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -814,22 +844,30 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     } else {
       if ((e = tc_get(h, &w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
       w->slot_cap = cap;
+      w->fp16 = false;  // arbitrary CV_32F descriptors: bf16 keeps the fp32 exponent range
       if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
       LaunchScope ls(h, KID_TC_PREP);
-      k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap);
+      k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap, 0);
     }
     if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
+    int idx_bits = 7;
+    while ((1 << idx_bits) < cap) ++idx_bits;
+    if (idx_bits > kMaxIdxBits) return cudaErrorInvalidValue;
+    const uint32_t idx_mask = (1u << idx_bits) - 1u;
+    const float key_rel = 1.0f / (float)(1u << (23 - idx_bits));
+    const float eps_rel = w->fp16 ? kEpsRelFp16 : kEpsRelBf16;
     const size_t smem = 1024 + (size_t)(1 + kStages) * kNumKB * kTileBytes + sizeof(TcShared);
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_GEMM);
-      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap);
+      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
+                                                                 make_idesc(w->fp16), idx_mask);
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
       k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
                                                      cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count,
-                                                     w->fb_list, h->counters);
+                                                     w->fb_list, h->counters, eps_rel, idx_mask, key_rel);
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
