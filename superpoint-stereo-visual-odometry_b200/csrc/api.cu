@@ -135,6 +135,11 @@ int spvo_destroy(spvo_handle hh) {
     cudaEventDestroy(r.b);
   }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+    if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
+  }
+  if (h->aux_fork) cudaEventDestroy(h->aux_fork);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SPVO_OK;

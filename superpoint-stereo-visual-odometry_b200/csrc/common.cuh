@@ -121,6 +121,11 @@ struct Handle {
   int* st_sq2t = nullptr;
   uint8_t* st_skeep = nullptr;
   void* tc_ws = nullptr;  // TcWorkspace (match_tc.cu)
+  // decode sub-batching (decode.cu: launch_decode)
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t aux_done[2] = {nullptr, nullptr};
+  cudaEvent_t aux_fork = nullptr;
+  int decode_subbatches = 0;  // 0 = automatic
   long long launches = 0;
   // optional per-kernel profile
   bool profiling = false;

@@ -12,6 +12,8 @@
 //
 // HBM-bound integer/float streaming work: coalesced 128 B channel-plane reads of semi, 32 B-aligned
 // float4 heatmap stores, warp-shuffle reductions; no tensor cores here.
+#include <stdlib.h>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -708,28 +710,38 @@ static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4 + cells * 4 + (size_t)cap * 2 + (size_t)cap;
 }
 
-cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
-                          const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                          float* scores, const TcSink* sink) {
+// One contiguous range of images [b0, b0 + B) on the handle's CURRENT stream (h->stream).
+static cudaError_t launch_decode_range(Handle* h, const float* semi, const float* desc, int b0, int B, int H, int W,
+                                       const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
+                                       float* scores, const TcSink* sink) {
   cudaStream_t st = h->stream;
   const int Hc = H / 8, Wc = W / 8, cells = Hc * Wc, K = cfg.max_keypoints;
   cudaError_t e;
-  if (B == 0) return cudaSuccess;
-  if ((e = cudaMemsetAsync(h->hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
+  semi += (size_t)b0 * 65 * cells;
+  if (desc) desc += (size_t)b0 * 256 * cells;
+  kpts += (size_t)b0 * K;
+  if (desc_out) desc_out += (size_t)b0 * K * 256;
+  n_out += b0;
+  if (scores) scores += (size_t)b0 * K;
+  float* heat = h->heat + (size_t)b0 * H * W;
+  unsigned* hist = h->hist + (size_t)b0 * kHistBins;
+  if ((e = cudaMemsetAsync(hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
   dim3 g1((cells + 31) / 32, B);
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
-    k_softmax_heat<<<g1, 256, 0, st>>>(semi, h->heat, h->hist, Hc, Wc, cfg.conf_thresh);
+    k_softmax_heat<<<g1, 256, 0, st>>>(semi, heat, hist, Hc, Wc, cfg.conf_thresh);
   }
   if (K > 0) {
     DetectParams p;
-    p.heat = h->heat; p.hist = h->hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
+    p.heat = heat; p.hist = hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
     const int plane_pitch = (cells + 4 + 3) & ~3;
     const size_t smem_planes = (size_t)kCP * plane_pitch * sizeof(float);
     const bool streaming = desc && desc_out && h->desc_tmp && h->kp_par && smem_planes <= 200 * 1024;
-    p.kp_par = streaming ? h->kp_par : nullptr;
+    int4* kp_par = streaming ? h->kp_par + (size_t)b0 * K : nullptr;
+    float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * K : nullptr;
+    p.kp_par = kp_par;
     p.cap = K <= 1536 ? 4096 : 8192;
     p.target = min(p.cap * 3 / 4, K + K / 2 + 256);
     const size_t smem = detect_smem_bytes(H, W, K, p.cap);
@@ -744,17 +756,20 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
         return e;
       {
         LaunchScope ls(h, KID_DESC_PLANES);
-        k_desc_planes<<<dim3(256 / kCP, B), 256, smem_planes, st>>>(desc, h->kp_par, n_out, h->desc_tmp, cells, K, plane_pitch);
+        k_desc_planes<<<dim3(256 / kCP, B), 256, smem_planes, st>>>(desc, kp_par, n_out, tmp, cells, K, plane_pitch);
       }
       {
-        LaunchScope ls(h, KID_DESC_NORM);
         TcSink sk;
         if (sink) {
           sk = *sink;
+          sk.xb = reinterpret_cast<unsigned short*>(sk.xb) + (size_t)b0 * sk.cap * 256;
+          sk.nrm += (size_t)b0 * sk.cap;
+          sk.opmax += b0;
           if ((e = cudaMemsetAsync(sk.opmax, 0, (size_t)B * sizeof(unsigned), st)) != cudaSuccess) return e;
         }
         const int rows = sk.xb ? sk.cap : K;
-        k_desc_normalize<<<dim3((rows + 31) / 32, B), 256, 0, st>>>(h->desc_tmp, n_out, desc_out, K, sk);
+        LaunchScope ls(h, KID_DESC_NORM);
+        k_desc_normalize<<<dim3((rows + 31) / 32, B), 256, 0, st>>>(tmp, n_out, desc_out, K, sk);
       }
     } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);
@@ -765,6 +780,43 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
     if ((e = cudaMemsetAsync(n_out, 0, (size_t)B * sizeof(int), st)) != cudaSuccess) return e;
   }
   return cudaGetLastError();
+}
+
+// Large batches are decoded as sub-batches alternating over two auxiliary streams: the intermediates of a
+// sub-batch (heatmap, un-normalised descriptors) then stay L2-resident between its kernels, and the
+// latency-bound per-image k_detect of one sub-batch overlaps the bandwidth-bound kernels of the other.
+cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
+                          const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
+                          float* scores, const TcSink* sink) {
+  if (B == 0) return cudaSuccess;
+  int nsb = h->decode_subbatches > 0 ? h->decode_subbatches : 1;  // measured on B200: 2 sub-batches gain 1.5 %, more lose (k_detect is latency-bound per image)
+  if (const char* env = getenv("SPVO_DECODE_SUBBATCHES")) nsb = atoi(env) > 0 ? atoi(env) : nsb;  // tuning knob
+  if (nsb > B) nsb = B;
+  if (nsb <= 1) return launch_decode_range(h, semi, desc, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+  cudaError_t e;
+  if (!h->aux_stream[0]) {
+    for (int i = 0; i < 2; ++i) {
+      if ((e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  cudaStream_t main_st = h->stream;
+  if ((e = cudaEventRecord(h->aux_fork, main_st)) != cudaSuccess) return e;
+  for (int i = 0; i < 2; ++i)
+    if ((e = cudaStreamWaitEvent(h->aux_stream[i], h->aux_fork, 0)) != cudaSuccess) return e;
+  cudaError_t rc = cudaSuccess;
+  for (int sb = 0; sb < nsb && rc == cudaSuccess; ++sb) {
+    const int b0 = (int)((long long)B * sb / nsb), b1 = (int)((long long)B * (sb + 1) / nsb);
+    h->stream = h->aux_stream[sb & 1];
+    rc = launch_decode_range(h, semi, desc, b0, b1 - b0, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+  }
+  h->stream = main_st;
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventRecord(h->aux_done[i], h->aux_stream[i])) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(main_st, h->aux_done[i], 0)) != cudaSuccess) return e;
+  }
+  return rc;
 }
 
 size_t decode_smem_required(int H, int W, int K) { return detect_smem_bytes(H, W, K, K <= 1536 ? 4096 : 8192); }

@@ -570,15 +570,27 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
     }
     float v[3] = {INFINITY, INFINITY, INFINITY};
     int ix[3] = {-1, -1, -1};
-    constexpr int kU = 4;  // columns in flight per warp
-    for (int jb = warp; jb < Nb; jb += 8 * kU) {
-      float4 xs[kU], ys[kU];
+    constexpr int kU = 4;  // columns per step; the next step's loads are issued before this step's math
+    float4 xs[kU], ys[kU], xn[kU], yn[kU];
+    float nbs[kU], nbn[kU];
+    auto load_cols = [&](int jb, float4* x, float4* y, float* nb) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int j = min(jb + 8 * u, Nb - 1);
-        xs[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
-        ys[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
+        x[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
+        y[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
+        nb[u] = __ldg(nbv + j);
       }
+    };
+    if (warp < Nb) load_cols(warp, xn, yn, nbn);
+    for (int jb = warp; jb < Nb; jb += 8 * kU) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        xs[u] = xn[u];
+        ys[u] = yn[u];
+        nbs[u] = nbn[u];
+      }
+      if (jb + 8 * kU < Nb) load_cols(jb + 8 * kU, xn, yn, nbn);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int j = jb + 8 * u;
@@ -610,7 +622,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
         q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
         if (j < Nb) {
-          const float g = __fmaf_rn(-2.0f, q1, nbv[j]);
+          const float g = __fmaf_rn(-2.0f, q1, nbs[u]);
           if (g < v[2]) {
             if (g < v[1]) {
               v[2] = v[1]; ix[2] = ix[1];
