@@ -463,7 +463,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_tc_fill_dist", "k_desc_planes", "k_desc_normalize"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

@@ -24,7 +24,7 @@ struct Handle;
 // (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
 enum KernelId {
   KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
-  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_DESC_PLANES, KID_DESC_NORM, KID_COUNT
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_COUNT
 };
 struct ProfRec {
   int kid;

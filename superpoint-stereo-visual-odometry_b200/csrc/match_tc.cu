@@ -353,6 +353,60 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_tc_triage: one THREAD per row.  Most rows are decided by the bound alone -- the second shortlist
+// entry is farther than the bound from the first, so the first IS the exact nearest neighbour and no
+// distance has to be evaluated (its DMatch.distance is filled in later only if the match survives).
+// Everything else (>= 2 columns inside the bound, kNN rows, tiny column counts) is queued for the
+// warp-per-row k_tc_rerank.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm,
+            const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
+            int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
+            int* __restrict__ rr_count, int* __restrict__ rr_list, float eps_rel, uint32_t idx_mask, float key_rel) {
+  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
+  const bool rev = dp >= P;
+  const MatchProblem pr = probs[p];
+  const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
+  const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= Na) return;
+  bool resolved = false;
+  int j0 = -1;
+  if (Nb == 0) {
+    resolved = true;
+  } else if (Nb > kTop && !(mode == SPVO_MATCH_KNN_RATIO && !rev)) {
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    const float na = nrm[(size_t)a_op * cap + i];
+    const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
+    const float off = key_offset(amax, bmax);
+    const float g0 = __uint_as_float(k0 & ~idx_mask) - off, g1 = __uint_as_float(k1 & ~idx_mask) - off;
+    const float eps = eps_rel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
+    const float slack = 2.0f * eps + key_rel * (g0 + 2.0f * eps + off) * 1.01f;
+    if (g1 > g0 + slack) {  // same test as k_tc_rerank's nc == 1
+      resolved = true;
+      j0 = (int)(k0 & idx_mask);
+    }
+  }
+  if (resolved) {
+    if (!rev) {
+      const size_t o = ((size_t)p * max_rows + i) * 2;
+      row_best[o] = j0;
+      row_best[o + 1] = -1;
+      row_d[o] = -1.0f;  // "not evaluated yet" (k_tc_fill_dist)
+      row_d[o + 1] = INFINITY;
+    } else {
+      col_best[(size_t)p * max_cols + i] = j0;
+    }
+  } else {
+    rr_list[(size_t)dp * cap + atomicAdd(&rr_count[dp], 1)] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_tc_rerank: one warp per row of a directed problem.  Two (row, column) pairs are evaluated at a
 // time, 16 lanes each: lane (k = l16/4, l = l16%4) owns OpenCV's accumulator s[k][l].
 // ------------------------------------------------------------------------------------------------
@@ -389,7 +443,8 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
             const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
             int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
             int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
-            float eps_rel, uint32_t idx_mask, float key_rel) {
+            float eps_rel, uint32_t idx_mask, float key_rel, const int* __restrict__ rr_count,
+            const int* __restrict__ rr_list) {
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -397,12 +452,16 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   const float* A = rev ? pr.t : pr.q;
   const float* B = rev ? pr.q : pr.t;
   const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-  if (i >= Na) return;
+  const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int n_rr = rr_count[dp];
+  // only the rows k_tc_triage queued; a few blocks per directed problem stride over its list
+  for (int li = blockIdx.x * 8 + (threadIdx.x >> 5); li < n_rr; li += gridDim.x * 8) {
+  const int i = rr_list[(size_t)dp * cap + li];
   float b0 = INFINITY, b1 = INFINITY;
   int x0 = INT_MAX, x1 = INT_MAX;
   bool full = false;
   const float* arow = A + (size_t)i * kDim;
+  (void)Na;
   if (Nb > 0) {
     // merge the two per-half shortlists: the kTop smallest packed keys of the row
     const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
@@ -464,7 +523,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
         fb_list[(size_t)dp * cap + atomicAdd(&fb_count[dp], 1)] = i;
         atomicAdd(&counters[1], 1ull);
       }
-      return;
+      continue;
     } else if (nc == 1 && !knn) {
       // the nearest neighbour is proved without evaluating any distance; DMatch.distance is filled in
       // by k_tc_fill_dist only for the matches that survive (marker: negative distance)
@@ -497,6 +556,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
     } else {
       col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
     }
+  }
   }
 }
 
@@ -736,6 +796,8 @@ struct TcWorkspace {
   uint32_t* top_key = nullptr;
   int* fb_count = nullptr;
   int* fb_list = nullptr;
+  int* rr_count = nullptr;  // rows queued by k_tc_triage for k_tc_rerank
+  int* rr_list = nullptr;
   size_t rows = 0, ops = 0, top_rows = 0;
   int slot_cap = 0;  // rows per operand slot of the current layout
   bool fp16 = false; // operand format of the current contents (false: bf16)
@@ -770,7 +832,12 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
     if (w->top_key) cudaFree(w->top_key);
     if (w->fb_count) cudaFree(w->fb_count);
     if (w->fb_list) cudaFree(w->fb_list);
-    w->top_key = nullptr; w->fb_count = nullptr; w->fb_list = nullptr; w->top_rows = 0;
+    if (w->rr_count) cudaFree(w->rr_count);
+    if (w->rr_list) cudaFree(w->rr_list);
+    w->top_key = nullptr; w->fb_count = nullptr; w->fb_list = nullptr; w->rr_count = nullptr; w->rr_list = nullptr;
+    w->top_rows = 0;
+    if ((e = cudaMalloc((void**)&w->rr_count, top_rows * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->rr_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_count, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
@@ -782,7 +849,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
 void tc_workspace_free(Handle* h) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
   if (!w) return;
-  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_count, w->fb_list};
+  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_count, w->fb_list, w->rr_count, w->rr_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete w;
@@ -862,6 +929,7 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap, 0);
     }
     if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(w->rr_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
     int idx_bits = 7;
     while ((1 << idx_bits) < cap) ++idx_bits;
     if (idx_bits > kMaxIdxBits) return cudaErrorInvalidValue;
@@ -876,10 +944,17 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
                                                                  make_idesc(w->fp16), idx_mask);
     }
     {
+      LaunchScope ls(h, KID_TC_TRIAGE);
+      k_tc_triage<<<dim3((cap + 255) / 256, ndir), 256, 0, st>>>(probs, P, cfg.mode, w->nrm, w->opmax, w->top_key, cap,
+                                                               mr, mc, h->row_best, h->row_d, h->col_best, w->rr_count,
+                                                               w->rr_list, eps_rel, idx_mask, key_rel);
+    }
+    {
       LaunchScope ls(h, KID_TC_RERANK);
-      k_tc_rerank<<<dim3(cap / 8, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
+      k_tc_rerank<<<dim3(4, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
                                                      cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count,
-                                                     w->fb_list, h->counters, eps_rel, idx_mask, key_rel);
+                                                     w->fb_list, h->counters, eps_rel, idx_mask, key_rel, w->rr_count,
+                                                     w->rr_list);
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
