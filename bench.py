@@ -57,6 +57,19 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.proc = None
+        self.nvml = None
+        try:  # NVML polling (5 ms) resolves timed regions far shorter than nvidia-smi's loop period
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys))
+            self.samples, self.reason_bits, self._stop = [], 0, False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -72,7 +85,30 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def _poll(self):
+        nv, hd = self.nvml
+        while not self._stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                self.reason_bits |= nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def stop(self):
+        if self.nvml:
+            nv, hd = self.nvml
+            self._stop = True
+            self.t.join(timeout=1)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                     "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
+            reasons = sorted(n for n, bit in names.items() if self.reason_bits & bit)
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": mx,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml 5 ms poll during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -337,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=74, help="stereo pairs per batch (2F = 148 images = one CTA per SM in k_detect)")

@@ -200,7 +200,7 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 constexpr int kNormRing = 4;  // tile ct's column norms live in slot ct % 4 (see the producer for why 4 is safe)
 struct __align__(16) TcShared {
   float nrm[kNormRing][kBN];
-  uint64_t a_full;
+  uint64_t a_full, a_empty;
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t acc_full[kStages], acc_empty[kStages];
   uint32_t tmem_base;
@@ -222,19 +222,36 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
   tmem_ld32(taddr + 32, r + 32);
 }
 
+// Work item = (directed problem dp, 128-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
+// items bid, bid + grid, ...; barriers and TMEM are set up once, and the B-tile / accumulator pipelines
+// run continuously across items (a global tile counter gives stage and phase), so only the A block
+// reload at an item boundary is exposed.
+struct TcItem {
+  int dp, rb, Na, Nb, a_op, b_op, nct;
+  bool valid;
+};
+__device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs, int P, int w, int nrb) {
+  TcItem it;
+  it.dp = w / nrb;
+  it.rb = w - it.dp * nrb;
+  const int p = it.dp < P ? it.dp : it.dp - P;
+  const bool rev = it.dp >= P;
+  const MatchProblem pr = probs[p];
+  it.Na = rev ? pr.M : pr.N;
+  it.Nb = rev ? pr.N : pr.M;
+  it.a_op = rev ? pr.b_op : pr.a_op;
+  it.b_op = rev ? pr.a_op : pr.b_op;
+  it.nct = (it.Nb + kBN - 1) / kBN;
+  it.valid = it.rb * kBM < it.Na;
+  return it;
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs, int P,
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
-          int cap, uint32_t idesc, uint32_t idx_mask) {
+          int cap, uint32_t idesc, uint32_t idx_mask, int n_items) {
   extern __shared__ uint8_t smem_raw[];
-  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
-  const bool rev = dp >= P;
-  const MatchProblem pr = probs[p];
-  const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
-  const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
-  const int rb = blockIdx.x;
-  if (rb * kBM >= Na) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
-  const int nct = (Nb + kBN - 1) / kBN;
+  const int nrb = cap / kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // carve shared memory: operands need 1024 B alignment for the 128 B swizzle
@@ -245,6 +262,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&sh->a_full), 1);
+    mbar_init(smem_u32(&sh->a_empty), 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&sh->b_full[s]), 1);
       mbar_init(smem_u32(&sh->b_empty[s]), 1);
@@ -266,82 +284,103 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 
   if (warp == 0) {
     // ===== TMA producer (one elected lane) =====
-    if (lane == 0 && nct > 0) {
-      const int a_row = a_op * cap + rb * kBM;
-      mbar_expect_tx(smem_u32(&sh->a_full), kNumKB * kTileBytes);
-      for (int kb = 0; kb < kNumKB; ++kb) tma_load_2d(sA + kb * kTileBytes, &tmap, smem_u32(&sh->a_full), kb * kKB, a_row);
-      for (int ct = 0; ct < nct; ++ct) {
-        const int s = ct % kStages, ph = (ct / kStages) & 1;
-        mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
-        mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes + kBN * 4);
-        const int b_row = b_op * cap + ct * kBN;
+    if (lane == 0) {
+      uint32_t gt = 0, ai = 0;  // global tile counter, count of items that loaded an A block
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const TcItem it = tc_item(probs, P, w, nrb);
+        if (!it.valid || it.nct == 0) continue;
+        mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A block
+        const int a_row = it.a_op * cap + it.rb * kBM;
+        mbar_expect_tx(smem_u32(&sh->a_full), kNumKB * kTileBytes);
         for (int kb = 0; kb < kNumKB; ++kb)
-          tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
-        // the tile's 128 column norms ride on the same barrier.  Slot ct % 4 is rewritten by tile ct+4, whose
-        // load waits for the MMAs of tile ct+2, which waited for the epilogue to drain tile ct: no race.
-        bulk_load_1d(smem_u32(&sh->nrm[ct % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, smem_u32(&sh->b_full[s]));
+          tma_load_2d(sA + kb * kTileBytes, &tmap, smem_u32(&sh->a_full), kb * kKB, a_row);
+        ++ai;
+        for (int ct = 0; ct < it.nct; ++ct, ++gt) {
+          const int s = gt % kStages, ph = (gt / kStages) & 1;
+          mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
+          mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes + kBN * 4);
+          const int b_row = it.b_op * cap + ct * kBN;
+          for (int kb = 0; kb < kNumKB; ++kb)
+            tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
+          // the tile's 128 column norms ride on the same barrier.  Slot gt % 4 is rewritten by tile gt+4, whose
+          // load waits for the MMAs of tile gt+2, which waited for the epilogue to drain tile gt: no race.
+          bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, smem_u32(&sh->b_full[s]));
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
-    if (lane == 0 && nct > 0) {
-      mbar_wait(smem_u32(&sh->a_full), 0);
-      for (int ct = 0; ct < nct; ++ct) {
-        const int s = ct % kStages, ph = (ct / kStages) & 1;
-        mbar_wait(smem_u32(&sh->acc_empty[s]), ph ^ 1);  // epilogue drained this accumulator
-        mbar_wait(smem_u32(&sh->b_full[s]), ph);         // TMA landed this B stage
-        tc_fence_after();
-        const uint32_t d = tmem_base + s * kBN;
+    if (lane == 0) {
+      uint32_t gt = 0, ai = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const TcItem it = tc_item(probs, P, w, nrb);
+        if (!it.valid || it.nct == 0) continue;
+        mbar_wait(smem_u32(&sh->a_full), ai & 1);
+        ++ai;
+        for (int ct = 0; ct < it.nct; ++ct, ++gt) {
+          const int s = gt % kStages, ph = (gt / kStages) & 1;
+          mbar_wait(smem_u32(&sh->acc_empty[s]), ph ^ 1);  // epilogue drained this accumulator
+          mbar_wait(smem_u32(&sh->b_full[s]), ph);         // TMA landed this B stage
+          tc_fence_after();
+          const uint32_t d = tmem_base + s * kBN;
 #pragma unroll
-        for (int kb = 0; kb < kNumKB; ++kb) {
+          for (int kb = 0; kb < kNumKB; ++kb) {
 #pragma unroll
-          for (int k = 0; k < kKB / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
-            const uint64_t bd = umma_desc_sw128(sB + (s * kNumKB + kb) * kTileBytes + k * 32);
-            tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
+            for (int k = 0; k < kKB / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
+              const uint64_t bd = umma_desc_sw128(sB + (s * kNumKB + kb) * kTileBytes + k * 32);
+              tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
+            }
           }
+          tc_commit(smem_u32(&sh->b_empty[s]));   // smem stage free once these MMAs retire
+          tc_commit(smem_u32(&sh->acc_full[s]));  // accumulator ready for the epilogue
         }
-        tc_commit(smem_u32(&sh->b_empty[s]));   // smem stage free once these MMAs retire
-        tc_commit(smem_u32(&sh->acc_full[s]));  // accumulator ready for the epilogue
+        tc_commit(smem_u32(&sh->a_empty));  // A block free once the item's last MMAs retire
       }
     }
   } else {
     // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; column half = (warp - 2) / 4 =====
     const int quad = warp & 3, half = (warp - 2) >> 2;
-    const int row = rb * kBM + quad * 32 + lane;
-    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    const float off = key_offset(__uint_as_float(opmax[a_op]), __uint_as_float(opmax[b_op]));
-    for (int ct = 0; ct < nct; ++ct) {
-      const int s = ct % kStages, ph = (ct / kStages) & 1;
-      const int j0 = ct * kBN + half * 64;
-      mbar_wait(smem_u32(&sh->acc_full[s]), ph);
-      tc_fence_after();
-      uint32_t acc[64];
-      tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
-      // the tile's column norms were bulk-copied to shared memory with its B operand (broadcast LDS.128)
-      float4 n4[16];
+    uint32_t gt = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const TcItem it = tc_item(probs, P, w, nrb);
+      if (!it.valid) continue;
+      const int row = it.rb * kBM + quad * 32 + lane;
+      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+      const float off = key_offset(__uint_as_float(opmax[it.a_op]), __uint_as_float(opmax[it.b_op]));
+      for (int ct = 0; ct < it.nct; ++ct, ++gt) {
+        const int s = gt % kStages, ph = (gt / kStages) & 1;
+        const int j0 = ct * kBN + half * 64;
+        mbar_wait(smem_u32(&sh->acc_full[s]), ph);
+        tc_fence_after();
+        uint32_t acc[64];
+        tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
+        // the tile's column norms were bulk-copied to shared memory with its B operand (broadcast LDS.128)
+        float4 n4[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[ct % kNormRing][half * 64 + 4 * e]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
+        for (int e = 0; e < 16; ++e)
+          n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][half * 64 + 4 * e]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
+        for (int e = 0; e < 16; ++e) {
+          const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
-          const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
-          const uint32_t key = (__float_as_uint(g) & ~idx_mask) | (uint32_t)(j0 + 4 * e + u);
-          top3_net(key, k0, k1, k2);
+          for (int u = 0; u < 4; ++u) {
+            // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
+            const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
+            const uint32_t key = (__float_as_uint(g) & ~idx_mask) | (uint32_t)(j0 + 4 * e + u);
+            top3_net(key, k0, k1, k2);
+          }
         }
       }
-    }
-    if (row < Na) {
-      uint32_t* o = top_key + (((size_t)dp * cap + row) * kLists + half) * kTop;
-      o[0] = k0;
-      o[1] = k1;
-      o[2] = k2;
+      if (row < it.Na) {
+        uint32_t* o = top_key + (((size_t)it.dp * cap + row) * kLists + half) * kTop;
+        o[0] = k0;
+        o[1] = k1;
+        o[2] = k2;
+      }
     }
   }
   tc_fence_before();
@@ -940,8 +979,10 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_GEMM);
-      k_tc_gemm<<<dim3(cap / kBM, ndir), kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
-                                                                 make_idesc(w->fp16), idx_mask);
+      const int n_items = (cap / kBM) * ndir;
+      const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
+      k_tc_gemm<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
+                                                make_idesc(w->fp16), idx_mask, n_items);
     }
     {
       LaunchScope ls(h, KID_TC_TRIAGE);
