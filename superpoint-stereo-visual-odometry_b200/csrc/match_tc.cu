@@ -363,6 +363,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
+        // tile-local shortlist first: the column-in-tile index is an immediate of the packing LOP3 (one ALU op
+        // per element instead of add + LOP3); the three survivors get the tile's column base OR-ed in afterwards
+        uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu, l2 = 0xFFFFFFFFu;
+        const uint32_t nmask = ~idx_mask;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
@@ -370,10 +374,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           for (int u = 0; u < 4; ++u) {
             // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
             const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
-            const uint32_t key = (__float_as_uint(g) & ~idx_mask) | (uint32_t)(j0 + 4 * e + u);
-            top3_net(key, k0, k1, k2);
+            const uint32_t key = (__float_as_uint(g) & nmask) | (uint32_t)(4 * e + u);
+            top3_net(key, l0, l1, l2);
           }
         }
+        // j0 is a multiple of 64 and the local index < 64, so OR == add; 0xFFFFFFFF (empty) stays the maximum
+        top3_net(l0 | (uint32_t)j0, k0, k1, k2);
+        top3_net(l1 | (uint32_t)j0, k0, k1, k2);
+        top3_net(l2 | (uint32_t)j0, k0, k1, k2);
       }
       if (row < it.Na) {
         uint32_t* o = top_key + (((size_t)it.dp * cap + row) * kLists + half) * kTop;
