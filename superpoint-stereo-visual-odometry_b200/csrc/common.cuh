@@ -84,6 +84,7 @@ struct Handle {
   // decode workspace
   float* heat = nullptr;          // [max_batch, max_h*max_w]
   unsigned* hist = nullptr;       // [max_batch, kHistBins]
+  float* cellmax = nullptr;       // [max_batch, cells] per-cell heatmap maximum
   float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)
   int4* kp_par = nullptr;         // [max_batch, max_k] sampling parameters
   unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)

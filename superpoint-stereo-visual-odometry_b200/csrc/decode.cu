@@ -31,9 +31,10 @@ namespace spvo {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
-               int Hc, int Wc, float conf) {
+               float* __restrict__ cellmax, int Hc, int Wc, float conf) {
   __shared__ float e_s[65][32];
   __shared__ float denom_s[32];
+  __shared__ float rowmax_s[8][32];
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -62,11 +63,24 @@ k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigne
     denom_s[lane] = __fadd_rn(s, 0.00001f);
   }
   __syncthreads();
-  if (!valid) return;
-  const float denom = denom_s[lane];
-  float p[8];
+  float p[8], pm = 0.0f;
+  if (valid) {
+    const float denom = denom_s[lane];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) p[j] = __fdiv_rn(e[j], denom);
+    for (int j = 0; j < 8; ++j) {
+      p[j] = __fdiv_rn(e[j], denom);
+      pm = fmaxf(pm, p[j]);
+    }
+  }
+  rowmax_s[grp][lane] = pm;
+  __syncthreads();
+  if (!valid) return;
+  if (grp == 0) {  // per-cell maximum: lets k_detect skip cells that cannot hold a first-chunk candidate
+    float cm = pm;
+#pragma unroll
+    for (int g = 1; g < 8; ++g) cm = fmaxf(cm, rowmax_s[g][lane]);
+    cellmax[(size_t)b * cells + cell] = cm;
+  }
   const int hc = cell / Wc, wc = cell - hc * Wc;
   const int W = Wc * 8;
   float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc + grp) * W + 8 * wc;
@@ -93,6 +107,7 @@ k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigne
 // ------------------------------------------------------------------------------------------------
 struct DetectParams {
   const float* heat;
+  const float* cellmax;  // [B, cells] per-cell maximum of the heatmap
   const unsigned* hist;
   int H, W;
   float conf;
@@ -184,6 +199,91 @@ __device__ int collect_keys(const float* heat, int H, int W, uint32_t conf_bits,
   return *s_count;
 }
 
+// First-chunk collection through the per-cell maxima: only cells whose maximum can reach the chunk's
+// lower bound are fetched (8 rows x 32 B each), instead of streaming the whole heatmap.  Returns the
+// number of keys >= lo (first `cap` stored), or -1 if more than `list_cap` cells qualify (caller then
+// falls back to the full scan).  hi is unbounded here.
+__device__ int collect_keys_cells(const float* __restrict__ heat, const float* __restrict__ cellmax, int H, int W,
+                                  uint32_t conf_bits, u64 lo, u64* keys, int cap, uint16_t* cell_list, int list_cap,
+                                  int* s_count, int* s_ncell) {
+  const int Wc = W >> 3, cells = (H >> 3) * Wc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    *s_count = 0;
+    *s_ncell = 0;
+  }
+  __syncthreads();
+  const uint32_t lo_b = (uint32_t)(lo >> 32);
+  for (int c0 = 0; c0 < cells; c0 += kDetectThreads) {
+    const int c = c0 + threadIdx.x;
+    bool q = false;
+    if (c < cells) {
+      const uint32_t mb = fbits(__ldg(cellmax + c));
+      q = mb > conf_bits && mb >= lo_b;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, q);
+    if (m) {
+      int basei = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) basei = atomicAdd(s_ncell, __popc(m));
+      basei = __shfl_sync(0xffffffffu, basei, leader);
+      if (q) {
+        const int slot = basei + __popc(m & ((1u << lane) - 1u));
+        if (slot < list_cap) cell_list[slot] = (uint16_t)c;
+      }
+    }
+  }
+  __syncthreads();
+  const int ncell = *s_ncell;
+  if (ncell > list_cap) return -1;
+  // half a warp per cell: lane l16 reads row l16/2, float4 l16&1 of the cell's 8x8 block
+  const int l16 = lane & 15, half = lane >> 4, row = l16 >> 1, part = l16 & 1;
+  constexpr int kCU = 4;
+  const int per_iter = (kDetectThreads / 32) * 2 * kCU;
+  for (int base = 0; base < ncell; base += per_iter) {
+    float4 v[kCU];
+    int cx[kCU], cy[kCU];
+    bool ok[kCU];
+#pragma unroll
+    for (int u = 0; u < kCU; ++u) {
+      const int ci = base + (u * (kDetectThreads / 32) + warp) * 2 + half;
+      ok[u] = ci < ncell;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cx[u] = cy[u] = 0;
+      if (ok[u]) {
+        const int c = cell_list[ci];
+        const int hc = c / Wc, wc = c - hc * Wc;
+        cy[u] = 8 * hc + row;
+        cx[u] = 8 * wc + 4 * part;
+        v[u] = __ldg(reinterpret_cast<const float4*>(heat + (size_t)cy[u] * W + cx[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kCU; ++u) {
+      const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t bts = fbits(pv[e]);
+        const u64 key = make_key(bts, cx[u] + e, cy[u], H);
+        const bool s = ok[u] && bts > conf_bits && key >= lo;
+        const unsigned m = __ballot_sync(0xffffffffu, s);
+        if (m) {
+          int basei = 0;
+          const int leader = __ffs(m) - 1;
+          if (lane == leader) basei = atomicAdd(s_count, __popc(m));
+          basei = __shfl_sync(0xffffffffu, basei, leader);
+          if (s) {
+            const int slot = basei + __popc(m & ((1u << lane) - 1u));
+            if (slot < cap) keys[slot] = key;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  return *s_count;
+}
+
 // Exact radix select: returns the m-th largest key among candidate keys < hi (unique keys), or
 // `floor_key` when fewer than m remain.  8 passes of 8 bits over the heatmap (slow path only).
 __device__ u64 radix_select(const float* heat, int H, int W, uint32_t conf_bits, u64 hi, int m, u64 floor_key,
@@ -264,7 +364,7 @@ __device__ void bitonic_sort_desc(u64* keys, int n_pad) {
 enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
 
-__global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
+__global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int H = p.H, W = p.W, K = p.K, cap = p.cap, d = p.dist, bd = p.border;
@@ -343,8 +443,14 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect(DetectParams p) {
 
   bool slow = false;
   // ---- chunk loop: consume candidates in descending key order ----------------------------------
+  bool first = true;
   while (true) {
-    int n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
+    int n = -1;
+    if (first && p.cellmax)  // first chunk (hi unbounded): fetch only the cells that can contribute
+      n = collect_keys_cells(heat, p.cellmax + (size_t)b * cells, H, W, conf_bits, lo, keys, cap, next, cap, &s_count,
+                             &s_want);
+    first = false;
+    if (n < 0) n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
     if (n > cap) {  // estimate too generous (or heavy ties): shrink the chunk exactly
       slow = true;
       __syncthreads();
@@ -725,15 +831,16 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
   if (scores) scores += (size_t)b0 * K;
   float* heat = h->heat + (size_t)b0 * H * W;
   unsigned* hist = h->hist + (size_t)b0 * kHistBins;
+  float* cellmax = h->cellmax + (size_t)b0 * cells;
   if ((e = cudaMemsetAsync(hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
   dim3 g1((cells + 31) / 32, B);
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
-    k_softmax_heat<<<g1, 256, 0, st>>>(semi, heat, hist, Hc, Wc, cfg.conf_thresh);
+    k_softmax_heat<<<g1, 256, 0, st>>>(semi, heat, hist, cellmax, Hc, Wc, cfg.conf_thresh);
   }
   if (K > 0) {
     DetectParams p;
-    p.heat = heat; p.hist = hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
+    p.heat = heat; p.cellmax = cellmax; p.hist = hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
     const int plane_pitch = (cells + 4 + 3) & ~3;
