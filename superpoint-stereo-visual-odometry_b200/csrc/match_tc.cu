@@ -1000,7 +1000,7 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
-      k_tc_rerank<<<dim3(4, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
+      k_tc_rerank<<<dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
                                                      cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count,
                                                      w->fb_list, h->counters, eps_rel, idx_mask, key_rel, w->rr_count,
                                                      w->rr_list);
