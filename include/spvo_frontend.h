@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPVO_ABI_VERSION 1
+#define SPVO_ABI_VERSION 2
 
 #define SPVO_DESC_DIM 256      /* output_desc_channel_, HPP:359 */
 #define SPVO_DET_CHANNELS 65   /* output_det_channel_,  HPP:355 */
@@ -170,6 +170,10 @@ int spvo_stereo_filter_batch_device(spvo_handle h, const spvo_keypoint* kpts_bas
  * first frame (visual_odometry_node.cpp:188-193).
  *   semi [F,2,65,H/8,W/8], desc [F,2,256,H/8,W/8]: image index 2f + eye, eye 0 = left (the batch-2
  *   layout of NN:480-484).  2F <= max_batch of the handle.  K = cfg->decode.max_keypoints. */
+typedef struct spvo_quad { /* indices into the four keypoint lists of BASE:163-196 */
+  int32_t curr_left, curr_right, prev_left, prev_right;
+} spvo_quad;
+
 typedef struct spvo_stereo_cfg {
   spvo_decode_cfg decode;
   spvo_match_cfg match;
@@ -185,6 +189,12 @@ typedef struct spvo_stereo_out { /* all device pointers (_device form) or all ho
   int* n_matches;        /* [2F]                                                                  */
   int* q2t;              /* [2F, K] maps_of_indices (HPP:161), -1 = unmatched                     */
   uint8_t* stereo_keep;  /* [F, K]  1 = L<->R match m passes BASE:169-172                         */
+  /* optional (may be NULL; need q2t and stereo_keep): per frame, the keypoint index quadruples that
+   * solveStereoOdometry triangulates (BASE:156-207): walk the L<->R matches in order, keep a match iff the
+   * current left keypoint also has a temporal match, the match passes the stereo test, and the matched
+   * previous left keypoint had a stereo match in the previous frame. */
+  struct spvo_quad* quads; /* [F, K] */
+  int* n_quads;            /* [F]    */
 } spvo_stereo_out;
 
 int spvo_stereo_reset(spvo_handle h);

@@ -56,6 +56,8 @@ def lib():
                                         C.c_int]
         L.spvo_oracle_stereo_filter.restype = C.c_int
         L.spvo_oracle_stereo_filter.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
+        L.spvo_oracle_consistency.restype = C.c_int
+        L.spvo_oracle_consistency.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -140,3 +142,14 @@ def stereo_filter(kl, kr, matches, stereo_threshold=2.0, min_disparity=0.25) -> 
     lib().spvo_oracle_stereo_filter(_p(kl), _p(kr), _p(m), len(m), float(stereo_threshold),
                                     float(min_disparity), _p(keep))
     return keep[: len(m)].astype(bool)
+
+
+def consistency(stereo_matches, map_t, keep, map_prev) -> np.ndarray:
+    """Quadruples (currL, currR, prevL, prevR) of BASE:156-207; returns int32 [n, 4]."""
+    m = np.ascontiguousarray(stereo_matches, DMATCH_DTYPE)
+    mt = np.ascontiguousarray(map_t, np.int32)
+    mp = np.ascontiguousarray(map_prev, np.int32)
+    kp = np.ascontiguousarray(keep, np.uint8)
+    out = np.zeros((max(len(m), 1), 4), np.int32)
+    n = lib().spvo_oracle_consistency(_p(m), len(m), _p(mt), _p(kp), _p(mp), _p(out))
+    return out[:n].copy()

@@ -421,4 +421,27 @@ int spvo_oracle_stereo_filter(const spvo_keypoint* kl, const spvo_keypoint* kr, 
   return 0;
 }
 
+// Post-match consistency walk of solveStereoOdometry (feature_detection_base.cpp:156-207): for each L<->R
+// match in list order keep (currL, currR, prevL, prevR) iff the current left keypoint has a temporal match
+// (:160), the stereo test passes (:169-172, given as keep[]), and the matched previous-left keypoint had a
+// stereo match in the previous frame (:181).  map_t = maps_of_indices[CURR_LEFT_PREV_LEFT],
+// map_prev = maps_of_indices[PREV_LEFT_PREV_RIGHT].  Returns the number of quadruples written.
+int spvo_oracle_consistency(const spvo_dmatch* stereo, int n, const int* map_t, const uint8_t* keep,
+                            const int* map_prev, int* quads_out) {
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const int il = stereo[i].queryIdx;
+    if (map_t[il] == -1) continue;
+    if (!keep[i]) continue;
+    const int ipl = map_t[il];
+    if (map_prev[ipl] == -1) continue;
+    quads_out[4 * k + 0] = il;
+    quads_out[4 * k + 1] = stereo[i].trainIdx;
+    quads_out[4 * k + 2] = ipl;
+    quads_out[4 * k + 3] = map_prev[ipl];
+    ++k;
+  }
+  return k;
+}
+
 }  // extern "C"

@@ -37,7 +37,8 @@ class StereoCfg(C.Structure):
 
 class StereoOut(C.Structure):
     _fields_ = [("kpts", C.c_void_p), ("desc", C.c_void_p), ("n_kpts", C.c_void_p), ("matches", C.c_void_p),
-                ("n_matches", C.c_void_p), ("q2t", C.c_void_p), ("stereo_keep", C.c_void_p)]
+                ("n_matches", C.c_void_p), ("q2t", C.c_void_p), ("stereo_keep", C.c_void_p), ("quads", C.c_void_p),
+                ("n_quads", C.c_void_p)]
 
 
 # every symbol include/spvo_frontend.h declares (checked by tests/test_abi.py against the header)

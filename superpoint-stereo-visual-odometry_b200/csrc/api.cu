@@ -127,7 +127,7 @@ int spvo_destroy(spvo_handle hh) {
   tc_workspace_free(h);
   void* ptrs[] = {h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
-                  h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n,
+                  h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -343,6 +343,7 @@ int spvo_stereo_reset(spvo_handle hh) {
   DeviceGuard g(h->device);
   h->has_prev = false;
   if (h->carry_n) CK(cudaMemsetAsync(h->carry_n, 0, sizeof(int), h->stream));
+  if (h->carry_map) CK(cudaMemsetAsync(h->carry_map, 0xFF, (size_t)(h->max_k > 0 ? h->max_k : 1) * sizeof(int), h->stream));
   return SPVO_OK;
 }
 
@@ -356,12 +357,16 @@ static int check_stereo_args(Handle* h, const float* semi, const float* desc, in
   int rc = check_decode_args(h, semi, 2 * F, H, W, &cfg->decode, out->kpts, out->n_kpts);
   if (rc) return rc;
   if (cfg->decode.max_keypoints < 1) return fail(h, SPVO_EINVAL, "stereo_batch: max_keypoints must be >= 1");
+  if ((out->quads || out->n_quads) && !(out->quads && out->n_quads && out->q2t && out->stereo_keep))
+    return fail(h, SPVO_EINVAL, "stereo_batch: quads need n_quads, q2t and stereo_keep outputs");
   return check_match_cfg(h, &cfg->match, SPVO_DESC_DIM);
 }
 
 static int ensure_carry(Handle* h) {
   if (h->carry_desc) return SPVO_OK;
   const size_t K = h->max_k > 0 ? h->max_k : 1;
+  CK(cudaMalloc((void**)&h->carry_map, K * sizeof(int)));
+  CK(cudaMemsetAsync(h->carry_map, 0xFF, K * sizeof(int), h->stream));
   CK(cudaMalloc((void**)&h->carry_desc, K * 256 * sizeof(float)));
   CK(cudaMalloc((void**)&h->carry_kpts, K * sizeof(spvo_keypoint)));
   CK(cudaMalloc((void**)&h->carry_n, sizeof(int)));
@@ -373,7 +378,8 @@ static int ensure_carry(Handle* h) {
 // The device pipeline shared by both forms.  desc_out must be a device buffer [2F,K,256].
 static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int F, int H, int W,
                            const spvo_stereo_cfg* cfg, spvo_keypoint* kpts, float* desc_out, int* n_kpts,
-                           spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep) {
+                           spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep, spvo_quad* quads,
+                           int* n_quads) {
   const int K = cfg->decode.max_keypoints;
   cudaStream_t st = h->stream;
   int rc = ensure_carry(h);
@@ -401,6 +407,9 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   if (keep)
     CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
                             cfg->min_disparity, keep));
+  if (quads) CK(launch_consistency(h, F, K, matches, n_matches, q2t, keep, h->carry_map, quads, n_quads));
+  if (q2t)  // previous frame's L<->R map for the next batch's first frame (BASE:475-481)
+    CK(cudaMemcpyAsync(h->carry_map, q2t + (size_t)(F - 1) * K, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
   // carry the last left image for the next batch's first temporal match
   const size_t last = (size_t)2 * (F - 1);
   CK(cudaMemcpyAsync(h->carry_desc, desc_out + last * K * 256, (size_t)K * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -421,7 +430,7 @@ int spvo_stereo_batch_device(spvo_handle hh, const float* semi, const float* des
   if (F == 0) return SPVO_OK;
   DeviceGuard g(h->device);
   return stereo_pipeline(h, semi, desc, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
-                         out->n_matches, out->q2t, out->stereo_keep);
+                         out->n_matches, out->q2t, out->stereo_keep, out->quads, out->n_quads);
 }
 
 int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
@@ -439,11 +448,14 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
     CK(cudaMalloc((void**)&h->st_snm, mb * sizeof(int)));
     CK(cudaMalloc((void**)&h->st_sq2t, mb * mk * sizeof(int)));
     CK(cudaMalloc((void**)&h->st_skeep, mb * mk));
+    CK(cudaMalloc((void**)&h->st_quads, mb * mk * sizeof(spvo_quad)));
+    CK(cudaMalloc((void**)&h->st_nquads, mb * sizeof(int)));
   }
   CK(cudaMemcpyAsync(h->st_semi, semi, B * 65 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->st_desc, desc, B * 256 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
   rc = stereo_pipeline(h, h->st_semi, h->st_desc, F, H, W, cfg, h->st_kpts, h->st_desc_out, h->st_n, h->st_smatches,
-                       h->st_snm, h->st_sq2t, out->stereo_keep ? h->st_skeep : nullptr);
+                       h->st_snm, h->st_sq2t, out->stereo_keep ? h->st_skeep : nullptr,
+                       out->quads ? h->st_quads : nullptr, h->st_nquads);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out->kpts, h->st_kpts, B * K * sizeof(spvo_keypoint), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(out->n_kpts, h->st_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -452,6 +464,10 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
   CK(cudaMemcpyAsync(out->n_matches, h->st_snm, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (out->q2t) CK(cudaMemcpyAsync(out->q2t, h->st_sq2t, B * K * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (out->stereo_keep) CK(cudaMemcpyAsync(out->stereo_keep, h->st_skeep, (size_t)F * K, cudaMemcpyDeviceToHost, st));
+  if (out->quads) {
+    CK(cudaMemcpyAsync(out->quads, h->st_quads, (size_t)F * K * sizeof(spvo_quad), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->n_quads, h->st_nquads, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
   return SPVO_OK;
 }
@@ -464,7 +480,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

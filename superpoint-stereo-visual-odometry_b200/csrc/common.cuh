@@ -24,7 +24,7 @@ struct Handle;
 // (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
 enum KernelId {
   KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
-  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_COUNT
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_CONSISTENCY, KID_COUNT
 };
 struct ProfRec {
   int kid;
@@ -69,6 +69,9 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
                                          int F, int K, int carry_slot);
+cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* matches, const int* n_matches,
+                               const int* q2t, const uint8_t* keep, const int* carry_map, spvo_quad* quads,
+                               int* n_quads);
 cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
 cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                  const int* q_slot, const int* t_slot, int P, int max_rows,
@@ -114,6 +117,9 @@ struct Handle {
   float* carry_desc = nullptr;      // [max_k, 256]
   spvo_keypoint* carry_kpts = nullptr;
   int* carry_n = nullptr;           // device int; 0 when there is no previous frame
+  int* carry_map = nullptr;         // [max_k] previous frame's L<->R index map (maps_of_indices[PREV_LEFT_PREV_RIGHT])
+  spvo_quad* st_quads = nullptr;    // host-form staging
+  int* st_nquads = nullptr;
   bool has_prev = false;
   bool carry_tc_valid = false;      // the carry's bf16 copy exists in the tensor matcher's carry slot
   // host-form staging of the stereo outputs

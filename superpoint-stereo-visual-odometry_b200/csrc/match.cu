@@ -292,6 +292,54 @@ __global__ void k_stereo_filter(const spvo_keypoint* __restrict__ kpts_base, int
   keep[(size_t)p * max_rows + m] = k;
 }
 
+// Post-match consistency (BASE:156-207): the quadruples solveStereoOdometry triangulates.  Block = frame.
+//   stereo matches of frame f : matches row f        temporal map : q2t row F+f
+//   previous frame's L<->R map: q2t row f-1, or the carried map of the previous batch for f = 0
+__global__ void __launch_bounds__(1024)
+k_consistency(int F, int K, const spvo_dmatch* __restrict__ matches, const int* __restrict__ n_matches,
+              const int* __restrict__ q2t, const uint8_t* __restrict__ keep, const int* __restrict__ carry_map,
+              spvo_quad* __restrict__ quads, int* __restrict__ n_quads) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_matches[f];
+  const int* map_t = q2t + (size_t)(F + f) * K;
+  const int* map_prev = f > 0 ? q2t + (size_t)(f - 1) * K : carry_map;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int m = start + tid;
+    bool ok = false;
+    spvo_quad qd;
+    qd.curr_left = qd.curr_right = qd.prev_left = qd.prev_right = -1;
+    if (m < n) {
+      const spvo_dmatch dm = matches[(size_t)f * K + m];
+      const int ipl = map_t[dm.queryIdx];                       // BASE:160
+      if (ipl >= 0 && keep[(size_t)f * K + m]) {                // BASE:169-172
+        const int ipr = map_prev[ipl];                          // BASE:181
+        if (ipr >= 0) {
+          ok = true;
+          qd.curr_left = dm.queryIdx; qd.curr_right = dm.trainIdx; qd.prev_left = ipl; qd.prev_right = ipr;
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (ok) quads[(size_t)f * K + off + __popc(bal & ((1u << lane) - 1u))] = qd;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) n_quads[f] = s_base;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
@@ -377,6 +425,15 @@ cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const f
     k_setup_stereo_problems<<<(2 * F + 127) / 128, 128, 0, h->stream>>>(probs, desc_out, n_out, h->carry_desc,
                                                                        h->carry_n, F, K, carry_slot);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* matches, const int* n_matches,
+                               const int* q2t, const uint8_t* keep, const int* carry_map, spvo_quad* quads,
+                               int* n_quads) {
+  if (F == 0) return cudaSuccess;
+  LaunchScope ls(h, KID_CONSISTENCY);
+  k_consistency<<<F, 1024, 0, h->stream>>>(F, K, matches, n_matches, q2t, keep, carry_map, quads, n_quads);
   return cudaGetLastError();
 }
 

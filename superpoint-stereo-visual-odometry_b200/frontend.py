@@ -173,7 +173,7 @@ class Frontend:
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
                                stereo_threshold, min_disparity)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
-                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep")])
+                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
         self._check(self._L.spvo_stereo_batch_device(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg),
                                                      C.byref(so)))
 
@@ -184,7 +184,7 @@ class Frontend:
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
                                stereo_threshold, min_disparity)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
-                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep")])
+                              ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
         self._check(self._L.spvo_stereo_batch(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg), C.byref(so)))
 
     @staticmethod
@@ -199,6 +199,8 @@ class Frontend:
             n_matches=torch.zeros(2 * F, dtype=torch.int32, **kw),
             q2t=torch.zeros(2 * F, K, dtype=torch.int32, **kw),
             stereo_keep=torch.zeros(F, K, dtype=torch.uint8, **kw),
+            quads=torch.zeros(F, K, 4, dtype=torch.int32, **kw),
+            n_quads=torch.zeros(F, dtype=torch.int32, **kw),
         )
         if with_desc:
             out["desc"] = torch.zeros(2 * F, K, 256, dtype=torch.float32, **kw)

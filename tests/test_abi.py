@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(spvo):
     for n in names:
         assert hasattr(L, n), f"{n} declared in spvo_frontend.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list and header disagree"
-    assert L.spvo_abi_version() == 1
+    assert L.spvo_abi_version() == 2
 
 
 def test_pod_layouts(spvo):
@@ -37,7 +37,7 @@ def test_pod_layouts(spvo):
         [0, 4, 8, 12, 16, 20, 24]
     assert [spvo.DMATCH_DTYPE.fields[n][1] for n in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
     assert C.sizeof(_lib.DecodeCfg) == 16 and C.sizeof(_lib.MatchCfg) == 16 and C.sizeof(_lib.StereoCfg) == 40
-    assert C.sizeof(_lib.StereoOut) == 7 * 8
+    assert C.sizeof(_lib.StereoOut) == 9 * 8
 
 
 def test_no_cpu_fallback_without_device(spvo):

@@ -19,12 +19,13 @@ def _oracle_stream(O, semi, desc, K, mode, thr, mind):
             mt, mapt = O.match(d["desc"][0, :nl], prev["desc"][0, : int(prev["n"][0])], mode=mode)
         else:
             mt, mapt = np.zeros(0, O.DMATCH_DTYPE), np.full(nl, -1, np.int32)
-        res.append(dict(dec=d, ms=ms, maps=maps, keep=keep, mt=mt, mapt=mapt))
+        quads = (O.consistency(ms, mapt, keep, res[-1]["maps"]) if res else np.zeros((0, 4), np.int32))
+        res.append(dict(dec=d, ms=ms, maps=maps, keep=keep, mt=mt, mapt=mapt, quads=quads))
         prev = d
     return res
 
 
-def _check_batch(S, out, ref, f0, F, K):
+def _check_batch(S, out, ref, f0, F, K, no_carry=False):
     kp = out["kpts"].view(S.KEYPOINT_DTYPE).reshape(2 * F, K)
     mm = out["matches"].view(S.DMATCH_DTYPE).reshape(2 * F, K)
     for f in range(F):
@@ -43,6 +44,10 @@ def _check_batch(S, out, ref, f0, F, K):
             assert (g["distance"].view(np.uint32) == m["distance"].view(np.uint32)).all()
             assert (out["q2t"][row, : len(mp)] == mp).all()
         assert (out["stereo_keep"][f, : len(r["keep"])].astype(bool) == r["keep"]).all()
+        if "quads" in out and not (f0 + f > 0 and f == 0 and no_carry):
+            nq = int(out["n_quads"][f])
+            assert nq == len(r["quads"]), (f, nq, len(r["quads"]))
+            assert (out["quads"][f, :nq] == r["quads"]).all()
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -68,6 +73,7 @@ def test_stereo_batch_host_and_device(spvo, oracle, mode):
     out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
     fe.stereo_batch(semi[F:2 * F], desc[F:2 * F], F, H, W, out, **kw)
     assert out["n_matches"][F] == 0 and out["n_matches"][F + 1] == len(ref[F + 1]["mt"])
+    assert out["n_quads"][0] == 0 and out["n_quads"][1] == len(ref[F + 1]["quads"]) > 20
     fe.close()
 
     # device-pointer form on the torch stream
