@@ -354,6 +354,56 @@ __device__ void bitonic_sort_desc(u64* keys, int n_pad) {
   }
 }
 
+// Smallest histogram bin index B >= bin_from such that 8 * (count of bins bin_from .. B) >= want_pixels
+// (the histogram holds one of every 8 pixels); kHistBins-1 if the whole tail is not enough.  Block-wide;
+// an ESTIMATE used to size a chunk -- exactness never depends on it.
+__device__ int hist_pick_bin(const unsigned* __restrict__ hist, int bin_from, int want_pixels, unsigned* s_warp_tot,
+                             int* s_bin) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int per = kHistBins / kDetectThreads;
+  if (tid == 0) *s_bin = kHistBins - 1;
+  unsigned loc[per], sum = 0;
+#pragma unroll
+  for (int i = 0; i < per; ++i) {
+    const int bin = tid * per + i;
+    loc[i] = bin >= bin_from ? hist[bin] : 0u;
+    sum += loc[i];
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp_tot[warp] = inc;
+  __syncthreads();
+  unsigned off = 0;
+  for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+  const unsigned excl = off + inc - sum;
+  const unsigned want = (unsigned)((want_pixels + 7) / 8);
+  if (excl < want && excl + sum >= want) {
+    unsigned c = excl;
+    for (int i = 0; i < per; ++i) {
+      c += loc[i];
+      if (c >= want) {
+        *s_bin = tid * per + i;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  return *s_bin;
+}
+
+// lower key bound (inclusive) of "all pixels whose histogram bin is <= bin"
+__device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
+  if (bin >= kHistBins - 1) return floor_key;
+  const uint32_t tb = kOneBits - ((uint32_t)(bin + 1) << kHistShift);  // bin(v) <= bin  <=>  bits > tb
+  const u64 lo = ((u64)tb + 1ull) << 32;
+  return lo < floor_key ? floor_key : lo;
+}
+
 // Exact greedy NMS, in parallel.  The reference walks candidates in rank order and keeps one iff no
 // earlier-kept candidate lies within its (2d+1)^2 box (NN:229-255).  Equivalently: candidate i is
 // KEPT iff every earlier-rank candidate inside its box is SUPPRESSED, and SUPPRESSED iff one of them
@@ -393,52 +443,10 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
   }
 
   // ---- first-chunk threshold from the sampled histogram (estimate only) ------------------------
-  {
-    const unsigned* hist = p.hist + (size_t)b * kHistBins;
-    constexpr int per = kHistBins / kDetectThreads;
-    unsigned loc[per], sum = 0;
-#pragma unroll
-    for (int i = 0; i < per; ++i) {
-      loc[i] = hist[tid * per + i];
-      sum += loc[i];
-    }
-    unsigned inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_warp_tot[warp] = inc;
-    __syncthreads();
-    unsigned off = 0;
-    for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
-    const unsigned excl = off + inc - sum;
-    const unsigned want = (unsigned)((p.target + 7) / 8);  // histogram holds 1 of every 8 pixels
-    if (excl < want && excl + sum >= want) {
-      unsigned c = excl;
-      for (int i = 0; i < per; ++i) {
-        c += loc[i];
-        if (c >= want) {
-          s_bin = tid * per + i;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-  }
+  const unsigned* hist = p.hist + (size_t)b * kHistBins;
+  int cur_bin = hist_pick_bin(hist, 0, p.target, s_warp_tot, &s_bin);
   u64 hi = ~0ull;
-  u64 lo;
-  {
-    const int bin = s_bin;
-    // bin(v) <= bin  <=>  bits > kOneBits - ((bin+1) << shift)
-    if (bin >= kHistBins - 1) {
-      lo = floor_key;
-    } else {
-      uint32_t tb = kOneBits - ((uint32_t)(bin + 1) << kHistShift);
-      lo = ((u64)tb + 1ull) << 32;
-      if (lo < floor_key) lo = floor_key;
-    }
-  }
+  u64 lo = bin_to_lo_key(cur_bin, floor_key);
   __syncthreads();
 
   bool slow = false;
@@ -569,7 +577,11 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
     }
     __syncthreads();
     hi = lo;
-    lo = radix_select(heat, H, W, conf_bits, hi, cap, floor_key, s_hist, &s_prefix, &s_want);
+    // size the next chunk from the histogram again (about 3/4 of the buffer); if the estimate overflows the
+    // buffer the loop's overflow branch shrinks it exactly with the radix select
+    cur_bin = hist_pick_bin(hist, cur_bin + 1, cap * 3 / 4, s_warp_tot, &s_bin);
+    lo = bin_to_lo_key(cur_bin, floor_key);
+    if (lo >= hi) lo = floor_key;  // cannot happen for increasing bins; keeps the loop finite regardless
     __syncthreads();
   }
 

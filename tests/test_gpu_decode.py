@@ -150,3 +150,26 @@ def test_decode_device_pointer_api_matches_host_api(spvo):
     assert (kp.cpu().numpy().view(np.uint8).reshape(B, K, 28) == r["kpts"].view(np.uint8).reshape(B, K, 28)).all()
     assert (do.cpu().numpy() == r["desc"]).all()
     fe.close()
+
+
+def test_decode_clustered_heatmap_long_walk(spvo, oracle):
+    """Realistic structure: candidates come in blobs, so the greedy walk visits many more candidates than it
+    keeps (several chunks of the key buffer); results must still equal the full sort + sequential walk."""
+    H, W, K = 240, 320, 700
+    rng = np.random.default_rng(42)
+    Hc, Wc = H // 8, W // 8
+    logit = np.full((H, W), -4.0, np.float32)
+    for _ in range(900):  # 5x5 blobs of nearly equal high logits
+        y, x = rng.integers(2, H - 3), rng.integers(2, W - 3)
+        logit[y - 2:y + 3, x - 2:x + 3] = 3.0 + 0.5 * rng.standard_normal((5, 5)).astype(np.float32)
+    semi = np.zeros((1, 65, Hc, Wc), np.float32)
+    semi[0, :64] = logit.reshape(Hc, 8, Wc, 8).transpose(1, 3, 0, 2).reshape(64, Hc, Wc)
+    semi[0, 64] = 0.0
+    _, desc = make_inputs(1, H, W, seed=2)
+    fe = spvo.Frontend(0, 1, H, W, 1000)
+    r, o = _compare(fe, oracle, semi, desc, max_keypoints=K)
+    assert o["n"][0] == K and o["walked"][0] > 4096, o["walked"]   # K reached only in the second key-buffer chunk
+    assert fe.debug_counters()[0] >= 1
+    r, o = _compare(fe, oracle, semi, desc, max_keypoints=1000)     # fewer survivors than K: every candidate walked
+    assert o["n"][0] < 1000 and o["walked"][0] == o["ncand"][0]
+    fe.close()
