@@ -141,6 +141,9 @@ int spvo_destroy(spvo_handle hh) {
     if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
   }
   if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 5; ++i)
+    if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SPVO_OK;
@@ -451,22 +454,60 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
     CK(cudaMalloc((void**)&h->st_quads, mb * mk * sizeof(spvo_quad)));
     CK(cudaMalloc((void**)&h->st_nquads, mb * sizeof(int)));
   }
-  CK(cudaMemcpyAsync(h->st_semi, semi, B * 65 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->st_desc, desc, B * 256 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = stereo_pipeline(h, h->st_semi, h->st_desc, F, H, W, cfg, h->st_kpts, h->st_desc_out, h->st_n, h->st_smatches,
-                       h->st_snm, h->st_sq2t, out->stereo_keep ? h->st_skeep : nullptr,
-                       out->quads ? h->st_quads : nullptr, h->st_nquads);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out->kpts, h->st_kpts, B * K * sizeof(spvo_keypoint), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out->n_kpts, h->st_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (out->desc) CK(cudaMemcpyAsync(out->desc, h->st_desc_out, B * K * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out->matches, h->st_smatches, B * K * sizeof(spvo_dmatch), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out->n_matches, h->st_snm, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (out->q2t) CK(cudaMemcpyAsync(out->q2t, h->st_sq2t, B * K * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (out->stereo_keep) CK(cudaMemcpyAsync(out->stereo_keep, h->st_skeep, (size_t)F * K, cudaMemcpyDeviceToHost, st));
-  if (out->quads) {
-    CK(cudaMemcpyAsync(out->quads, h->st_quads, (size_t)F * K * sizeof(spvo_quad), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->n_quads, h->st_nquads, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // The batch is processed as up to 4 chunks of consecutive frames: the H2D copy of chunk c+1 (copy stream)
+  // overlaps the kernels and the D2H of chunk c (compute stream).  Chunks continue the sequence through the
+  // handle's carry exactly like consecutive calls, so results do not depend on the chunking.
+  (void)B;
+  const int nchunk = F >= 16 ? 4 : 1;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; ++i) CK(cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(h->copy_ev[4], st));
+  CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[4], 0));
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t f0 = (size_t)F * c / nchunk, f1 = (size_t)F * (c + 1) / nchunk, nb = 2 * (f1 - f0);
+    CK(cudaMemcpyAsync(h->st_semi + 2 * f0 * 65 * cells, semi + 2 * f0 * 65 * cells, nb * 65 * cells * sizeof(float),
+                       cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->st_desc + 2 * f0 * 256 * cells, desc + 2 * f0 * 256 * cells, nb * 256 * cells * sizeof(float),
+                       cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->copy_ev[c], h->copy_stream));
+  }
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t f0 = (size_t)F * c / nchunk, f1 = (size_t)F * (c + 1) / nchunk, Fc = f1 - f0, nb = 2 * Fc;
+    CK(cudaStreamWaitEvent(st, h->copy_ev[c], 0));
+    // chunk-local device layout: images [2 f0, 2 f1); match rows [2 f0, 2 f0 + Fc) stereo, then Fc temporal
+    spvo_keypoint* d_kp = h->st_kpts + 2 * f0 * K;
+    float* d_desc = h->st_desc_out + 2 * f0 * K * 256;
+    int* d_n = h->st_n + 2 * f0;
+    spvo_dmatch* d_m = h->st_smatches + 2 * f0 * K;
+    int* d_nm = h->st_snm + 2 * f0;
+    int* d_q2t = h->st_sq2t + 2 * f0 * K;
+    uint8_t* d_keep = h->st_skeep + f0 * K;
+    spvo_quad* d_quads = h->st_quads + f0 * K;
+    int* d_nq = h->st_nquads + f0;
+    rc = stereo_pipeline(h, h->st_semi + 2 * f0 * 65 * cells, h->st_desc + 2 * f0 * 256 * cells, (int)Fc, H, W, cfg, d_kp,
+                         d_desc, d_n, d_m, d_nm, d_q2t, out->stereo_keep ? d_keep : nullptr,
+                         out->quads ? d_quads : nullptr, d_nq);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out->kpts + 2 * f0 * K, d_kp, nb * K * sizeof(spvo_keypoint), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->n_kpts + 2 * f0, d_n, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out->desc)
+      CK(cudaMemcpyAsync(out->desc + 2 * f0 * K * 256, d_desc, nb * K * 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // stereo rows -> [f0, f1), temporal rows -> [F + f0, F + f1) of the caller's whole-batch layout
+    for (int part = 0; part < 2; ++part) {
+      const size_t dst_row = (part ? (size_t)F : 0) + f0, src_row = part ? Fc : 0;
+      CK(cudaMemcpyAsync(out->matches + dst_row * K, d_m + src_row * K, Fc * K * sizeof(spvo_dmatch),
+                         cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(out->n_matches + dst_row, d_nm + src_row, Fc * sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (out->q2t)
+        CK(cudaMemcpyAsync(out->q2t + dst_row * K, d_q2t + src_row * K, Fc * K * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    if (out->stereo_keep) CK(cudaMemcpyAsync(out->stereo_keep + f0 * K, d_keep, Fc * K, cudaMemcpyDeviceToHost, st));
+    if (out->quads) {
+      CK(cudaMemcpyAsync(out->quads + f0 * K, d_quads, Fc * K * sizeof(spvo_quad), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(out->n_quads + f0, d_nq, Fc * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
   }
   CK(cudaStreamSynchronize(st));
   return SPVO_OK;

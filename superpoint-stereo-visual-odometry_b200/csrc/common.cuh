@@ -133,6 +133,9 @@ struct Handle {
   cudaEvent_t aux_done[2] = {nullptr, nullptr};
   cudaEvent_t aux_fork = nullptr;
   int decode_subbatches = 0;  // 0 = automatic
+  // host-form stereo batches: H2D of the next chunk overlaps compute of the current one
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   long long launches = 0;
   // optional per-kernel profile
   bool profiling = false;
