@@ -407,9 +407,9 @@ __device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
 // Exact greedy NMS, in parallel.  The reference walks candidates in rank order and keeps one iff no
 // earlier-kept candidate lies within its (2d+1)^2 box (NN:229-255).  Equivalently: candidate i is
 // KEPT iff every earlier-rank candidate inside its box is SUPPRESSED, and SUPPRESSED iff one of them
-// is KEPT.  Each round decides every candidate whose earlier-rank box neighbours are all decided;
-// states only move UNDECIDED -> KEPT/SUPPRESSED, so racing reads are harmless and the fixed point is
-// the sequential result.  Neighbours are found through a spatial hash of 8x8-pixel cells (linked
+// is KEPT.  Each (Jacobi) round decides every candidate whose earlier-rank box neighbours were all decided
+// in the previous rounds; states only move UNDECIDED -> KEPT/SUPPRESSED, at least the lowest-rank
+// undecided candidate is decided per round, and the fixed point is the sequential result.  Neighbours are found through a spatial hash of 8x8-pixel cells (linked
 // lists in shared memory).  Suppression by earlier chunks comes from the bitmap.
 enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
   unsigned* bitmap = reinterpret_cast<unsigned*>(emit + K);      // [H*ww]  pixels suppressed by earlier chunks
   int* head = reinterpret_cast<int*>(bitmap + H * ww);           // [cells] spatial hash: first candidate of a cell
   uint16_t* next = reinterpret_cast<uint16_t*>(head + cells);    // [cap]
-  uint8_t* state = reinterpret_cast<uint8_t*>(next + cap);       // [cap]
+  uint8_t* state = reinterpret_cast<uint8_t*>(next + cap);       // [2*cap] (second half: Jacobi double buffer)
   unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
   __shared__ int s_count, s_want, s_bin, s_emitted;
   __shared__ u64 s_prefix;
@@ -492,34 +492,49 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
         if (state[i] == ST_UNDEC) state[i] = ST_KEPT;
       __syncthreads();
     } else {
-      volatile uint8_t* vstate = state;
+      // Jacobi rounds: every round reads the previous round's states (st_in) and writes st_out, so there is no
+      // intra-round data race; the two byte arrays swap roles after each barrier.
+      uint8_t* st_in = state;
+      uint8_t* st_out = state + cap;
       while (true) {
         int undecided = 0;
         for (int i = tid; i < n; i += kDetectThreads) {
-          if (vstate[i] != ST_UNDEC) continue;
-          const uint32_t xy = (uint32_t)keys[i];
-          const int x = xy & 0xFFFF, y = xy >> 16;
-          const int cx0 = max(x - d, 0) >> 3, cx1 = min(x + d, W - 1) >> 3;
-          const int cy0 = max(y - d, 0) >> 3, cy1 = min(y + d, H - 1) >> 3;
-          bool kept = false, undec = false;
-          for (int cy = cy0; cy <= cy1; ++cy)
-            for (int cx = cx0; cx <= cx1; ++cx)
-              for (int q = head[cy * Wc + cx]; q >= 0 && q != kNil; q = next[q]) {
-                if (q < i) {
-                  const uint32_t qxy = (uint32_t)keys[q];
-                  const int qx = qxy & 0xFFFF, qy = qxy >> 16;
-                  if (abs(qx - x) <= d && abs(qy - y) <= d) {
-                    const uint8_t sq = vstate[q];
-                    kept |= sq == ST_KEPT;
-                    undec |= sq == ST_UNDEC;
+          const uint8_t si = st_in[i];
+          uint8_t so = si;
+          if (si == ST_UNDEC) {
+            const uint32_t xy = (uint32_t)keys[i];
+            const int x = xy & 0xFFFF, y = xy >> 16;
+            const int cx0 = max(x - d, 0) >> 3, cx1 = min(x + d, W - 1) >> 3;
+            const int cy0 = max(y - d, 0) >> 3, cy1 = min(y + d, H - 1) >> 3;
+            bool kept = false, undec = false;
+            for (int cy = cy0; cy <= cy1; ++cy)
+              for (int cx = cx0; cx <= cx1; ++cx)
+                for (int q = head[cy * Wc + cx]; q >= 0 && q != kNil; q = next[q]) {
+                  if (q < i) {
+                    const uint32_t qxy = (uint32_t)keys[q];
+                    const int qx = qxy & 0xFFFF, qy = qxy >> 16;
+                    if (abs(qx - x) <= d && abs(qy - y) <= d) {
+                      const uint8_t sq = st_in[q];
+                      kept |= sq == ST_KEPT;
+                      undec |= sq == ST_UNDEC;
+                    }
                   }
                 }
-              }
-          if (kept) vstate[i] = ST_SUPP;
-          else if (!undec) vstate[i] = ST_KEPT;
-          else ++undecided;
+            if (kept) so = ST_SUPP;
+            else if (!undec) so = ST_KEPT;
+            else ++undecided;
+          }
+          st_out[i] = so;
         }
-        if (__syncthreads_count(undecided > 0) == 0) break;
+        const int remaining = __syncthreads_count(undecided > 0);
+        uint8_t* t = st_in;
+        st_in = st_out;
+        st_out = t;
+        if (remaining == 0) break;
+      }
+      if (st_in != state) {  // final states must end up in state[]
+        for (int i = tid; i < n; i += kDetectThreads) state[i] = st_in[i];
+        __syncthreads();
       }
     }
 
@@ -825,7 +840,7 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
 static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   const int ww = (W + 31) >> 5;
   const size_t cells = (size_t)(H / 8) * (W / 8);
-  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4 + cells * 4 + (size_t)cap * 2 + (size_t)cap;
+  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4 + cells * 4 + (size_t)cap * 2 + (size_t)cap * 2;
 }
 
 // One contiguous range of images [b0, b0 + B) on the handle's CURRENT stream (h->stream).

@@ -201,6 +201,7 @@ constexpr int kNormRing = 4;  // tile ct's column norms live in slot ct % 4 (see
 struct __align__(16) TcShared {
   float nrm[kNormRing][kBN];
   uint64_t a_full, a_empty;
+  uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % 4
   uint64_t b_full[kStages], b_empty[kStages];
   uint64_t acc_full[kStages], acc_empty[kStages];
   uint32_t tmem_base;
@@ -263,6 +264,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&sh->a_full), 1);
     mbar_init(smem_u32(&sh->a_empty), 1);
+    for (int s = 0; s < kNormRing; ++s) mbar_init(smem_u32(&sh->nrm_full[s]), 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&sh->b_full[s]), 1);
       mbar_init(smem_u32(&sh->b_empty[s]), 1);
@@ -298,13 +300,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
           const int s = gt % kStages, ph = (gt / kStages) & 1;
           mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
-          mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes + kBN * 4);
+          mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes);
           const int b_row = it.b_op * cap + ct * kBN;
           for (int kb = 0; kb < kNumKB; ++kb)
             tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
-          // the tile's 128 column norms ride on the same barrier.  Slot gt % 4 is rewritten by tile gt+4, whose
-          // load waits for the MMAs of tile gt+2, which waited for the epilogue to drain tile gt: no race.
-          bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, smem_u32(&sh->b_full[s]));
+          // the tile's 128 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits on
+          // it directly).  The slot is rewritten by tile gt+4, whose load waits for the MMAs of tile gt+2, which
+          // waited for the epilogue to drain tile gt (norms already in registers): no overwrite race.
+          const uint32_t nb_bar = smem_u32(&sh->nrm_full[gt % kNormRing]);
+          mbar_expect_tx(nb_bar, kBN * 4);
+          bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, nb_bar);
         }
       }
     }
@@ -355,7 +360,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         tc_fence_after();
         uint32_t acc[64];
         tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
-        // the tile's column norms were bulk-copied to shared memory with its B operand (broadcast LDS.128)
+        // the tile's column norms were bulk-copied to shared memory next to its B operand (broadcast LDS.128)
+        mbar_wait(smem_u32(&sh->nrm_full[gt % kNormRing]), (gt / kNormRing) & 1);
         float4 n4[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e)
