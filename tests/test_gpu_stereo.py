@@ -103,3 +103,21 @@ def test_stereo_batch_algorithm_switch_keeps_the_carry(spvo, oracle):
                         algorithm=alg)
         _check_batch(S, out, ref, b * F, F, K)
     fe.close()
+
+
+def test_stereo_batch_host_chunked_path(spvo, oracle):
+    """F >= 16: the host-pointer call processes the batch as 4 chunks with overlapped H2D; the caller-visible
+    whole-batch layout (stereo rows 0..F-1, temporal rows F..2F-1, quadruples) must be unchanged."""
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, F = 64, 96, 60, 18
+    semi, desc = synth.make_stream(2 * F, H, W, seed=21, device="cpu")
+    semi, desc = semi.numpy(), desc.numpy()
+    ref = _oracle_stream(oracle, semi, desc, K, 1, 2.0, 0.25)
+    fe = S.Frontend(0, 2 * F, H, W, K)
+    for b in range(2):
+        out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
+        fe.stereo_batch(semi[b * F:(b + 1) * F], desc[b * F:(b + 1) * F], F, H, W, out, max_keypoints=K, mode=1)
+        _check_batch(S, out, ref, b * F, F, K)
+    assert sum(len(r["quads"]) for r in ref) > 50
+    fe.close()
