@@ -80,7 +80,8 @@ enum {
 enum {
   SPVO_MATCHER_AUTO = 0,
   SPVO_MATCHER_EXACT_FP32 = 1, /* CUDA-core kernel computing every distance in OpenCV's fp32 order */
-  SPVO_MATCHER_TENSOR = 2      /* tcgen05/TMEM bf16 GEMM shortlist + exact fp32 re-rank */
+  SPVO_MATCHER_TENSOR = 2      /* tcgen05/TMEM 16-bit GEMM shortlist (bf16; fp16 for the unit-norm descriptors
+                                  decode produces) + exact fp32 re-rank; identical results */
 };
 
 typedef struct spvo_match_cfg {
@@ -209,8 +210,9 @@ int spvo_stereo_batch(spvo_handle h, const float* semi, const float* desc, int F
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long spvo_kernel_launches(spvo_handle h);
 /* Counters of the last decode / match (device work must be complete: call spvo_sync first):
- * decode: [0] images that left the histogram fast path (slow exact path taken), match: [1] rows
- * re-ranked by the exact full-row fallback, [2] candidate pairs re-ranked exactly. */
+ * [0] images whose decode needed more than the first candidate chunk (exact multi-chunk path),
+ * [1] matcher rows sent to the fp32 full-row fallback, [2] rows that needed an exact scan of every column.
+ * Cumulative since spvo_create. */
 int spvo_debug_counters(spvo_handle h, long long* out, int n);
 
 /* Optional per-kernel profile: when enabled every kernel launch is bracketed by CUDA events on

@@ -5,24 +5,32 @@
 // feature_detection_base.cpp:434-500) -- but the N x M x 256 contraction runs on the 5th-gen
 // tensor cores:
 //
-//   k_tc_prep    fp32 descriptors -> bf16 rows + fp32 squared norms in a row-padded workspace
-//   k_tc_gemm    per (directed problem, 128-row block): S = A . B^T with tcgen05.mma
-//                (cta_group::1, M = N = 128, K = 16, bf16 x bf16 -> fp32 in TMEM), operands staged by
-//                TMA (128 B swizzle) through a 2-stage mbarrier pipeline, accumulators double
-//                buffered in TMEM; the epilogue warps read TMEM with tcgen05.ld and keep, per row,
-//                the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN REGISTERS
-//                (the distance matrix never exists in memory)
-//   k_tc_rerank  exact re-rank: every shortlisted column within a proved error bound of the row
-//                minimum gets its distance recomputed in OpenCV's fp32 operation order (bit-exact
-//                DMatch.distance, first-index ties); rows whose shortlist cannot be proved complete
-//                fall back to an exact scan of the whole row.  Match indices therefore stay
-//                bit-exact although the GEMM is bf16.
+//   k_tc_prep       fp32 descriptors -> 16-bit rows (bf16) + fp32 squared norms in a row-padded workspace.
+//                   Not used by the stereo pipeline: k_desc_normalize (decode.cu) writes fp16 operands of
+//                   its unit-norm descriptors straight into the workspace.
+//   k_tc_gemm       persistent, one CTA per SM over (directed problem, 128-row block) items:
+//                   S = A . B^T with tcgen05.mma (cta_group::1, M = N = 128, K = 16, 16-bit -> fp32 in
+//                   TMEM), B tiles staged by TMA (128 B swizzle) through a 2-stage mbarrier pipeline,
+//                   accumulators double buffered in TMEM; 8 epilogue warps read TMEM with tcgen05.ld and
+//                   keep, per row, the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN
+//                   REGISTERS as packed keys (the distance matrix never exists in memory)
+//   k_tc_triage     one thread per row: rows whose 2nd shortlist entry is outside the proved error bound
+//                   are decided with no further arithmetic; the rest are queued
+//   k_tc_rerank     queued rows: every shortlisted column within the bound gets its distance recomputed
+//                   in OpenCV's fp32 operation order (bit-exact DMatch.distance, first-index ties); rows
+//                   whose whole shortlist is inside the bound go to the fallback worklist
+//   k_tc_fallback   fp32 dot products of the queued rows against every column (8 rows per pass), then
+//                   exact distances for the columns within 2*eps32; if even that could be incomplete,
+//                   an exact scan of the whole row
+//   k_tc_fill_dist  exact DMatch.distance only for the matches that survive (cross-check)
+// Match indices therefore stay bit-exact although the GEMM runs in 16-bit.
 //
 // Error bound.  bf16 rounding (RN) has relative error <= 2^-9 per element, so
 // |a.b - bf16(a).bf16(b)| <= (2^-8 + 2^-18)|a||b|; fp32 accumulation of 256 exact products adds
-// <= 256 * 2^-22 |a||b|.  With eps = kEpsRel*|a||b| + kEpsAbs*(|a|^2+|b|^2) (kEpsRel = 0.0085 covers
-// 2x the dot-product bound), |approx d^2 - exact d^2| <= eps.  A column whose approx d^2 exceeds the
-// row minimum by more than 2*eps cannot be the exact minimum (nor tie with it).
+// <= 256 * 2^-22 |a||b|.  With eps = eps_rel*|a||b| + kEpsAbs*(|a|^2+|b|^2) (eps_rel = 0.0085 covers
+// 2x the dot-product bound; 0.0022 for fp16 operands, 2^-11 per element), |approx d^2 - exact d^2| <= eps.
+// A column whose approx d^2 exceeds the row minimum by more than 2*eps (plus the key truncation) cannot be
+// the exact minimum (nor tie with it).
 //
 // Cross-check needs the reverse nearest neighbour as well: it is a second directed problem
 // (B against A) in the same launch; D(a,b) is bitwise symmetric in OpenCV's arithmetic.
