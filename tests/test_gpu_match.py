@@ -132,3 +132,15 @@ def test_match_tensor_random_uses_fallback_and_stays_exact(spvo, oracle):
         _check(fe, oracle, q, t, mode, 2)
     print("fallback rows:", fe.debug_counters()[1])
     fe.close()
+
+
+def test_match_tensor_max_size_8192(spvo, oracle):
+    """Largest size of the packed shortlist index (13 bits): N = M = 8192, cross-check."""
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    base = unit_rows(8192, seed=99)
+    q, t = base, _noisy_copy(base, seed=5)
+    gm, gmap = fe.match(q, t, mode=1, algorithm=2)
+    om, omap = oracle.match(q, t, mode=1, num_threads=16)
+    assert len(gm) == len(om) > 7000 and (gm["queryIdx"] == om["queryIdx"]).all() and (gm["trainIdx"] == om["trainIdx"]).all()
+    assert (gm["distance"].view(np.uint32) == om["distance"].view(np.uint32)).all() and (gmap == omap).all()
+    fe.close()
