@@ -392,7 +392,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=74, help="stereo pairs per batch (2F = 148 images = one CTA per SM in k_detect)")
+    ap.add_argument("--pairs-per-step", type=int, default=148,
+                    help="stereo pairs per batch (2F = 296 images = two k_detect CTAs per SM)")
     ap.add_argument("--ring", type=int, default=3, help="distinct input batches cycled through (ring >> L2)")
     ap.add_argument("--algorithm", type=int, default=0, help="SPVO_MATCHER_* (0 auto, 1 exact fp32, 2 tensor)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -101,6 +101,7 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   ALLOC(h->heat, (size_t)max_batch * px * sizeof(float));
   ALLOC(h->hist, (size_t)max_batch * kHistBins * sizeof(unsigned));
   ALLOC(h->cellmax, (size_t)max_batch * cells * sizeof(float));
+  ALLOC(h->nms_bitmap, (size_t)max_batch * (px / 16 + 64) * sizeof(unsigned));  // H*ceil(W/32) <= H*W/16 for W >= 16
   ALLOC(h->counters, 8 * sizeof(unsigned long long));
   cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long));
   const size_t K = max_keypoints > 0 ? max_keypoints : 1;
@@ -125,7 +126,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};

@@ -117,6 +117,8 @@ struct DetectParams {
   int* n_out;
   unsigned long long* counters;
   int4* kp_par;   // [B,K] sampling parameters for k_desc_planes (may be NULL)
+  size_t bitmap_stride;  // words per image in `bitmap`
+  unsigned* bitmap;  // [B, bitmap_stride] global scratch: pixels suppressed by earlier chunks (multi-chunk path only)
   int cap;        // key buffer capacity (power of two)
   int target;     // candidates wanted in the first chunk
 };
@@ -414,7 +416,7 @@ __device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
 enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
 
-__global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
+__global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int H = p.H, W = p.W, K = p.K, cap = p.cap, d = p.dist, bd = p.border;
@@ -422,8 +424,11 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
   const int Hc = H >> 3, Wc = W >> 3, cells = Hc * Wc;
   u64* keys = reinterpret_cast<u64*>(smem_raw);                  // [cap]   sorted candidate keys of the chunk
   u64* emit = keys + cap;                                        // [K]     emitted keypoints (score | y<<16 | x)
-  unsigned* bitmap = reinterpret_cast<unsigned*>(emit + K);      // [H*ww]  pixels suppressed by earlier chunks
-  int* head = reinterpret_cast<int*>(bitmap + H * ww);           // [cells] spatial hash: first candidate of a cell
+  int* head = reinterpret_cast<int*>(emit + K);                  // [cells] spatial hash: first candidate of a cell
+  // pixels suppressed by EARLIER chunks live in a global-memory bitmap that only the multi-chunk path touches
+  // (zeroed lazily), which keeps the CTA at ~85 KB of shared memory: two images per SM
+  unsigned* bitmap = p.bitmap + (size_t)b * p.bitmap_stride;
+  bool have_bitmap = false;
   uint16_t* next = reinterpret_cast<uint16_t*>(head + cells);    // [cap]
   uint8_t* state = reinterpret_cast<uint8_t*>(next + cap);       // [2*cap] (second half: Jacobi double buffer)
   unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
@@ -436,7 +441,6 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
   const u64 floor_key = ((u64)conf_bits + 1ull) << 32;  // smallest possible candidate key (score > conf)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
   if (tid == 0) {
     s_emitted = 0;
     s_bin = kHistBins - 1;
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
       const uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
       const int x = (int)(pos / (uint32_t)H), y = (int)(pos - (uint32_t)x * (uint32_t)H);
       keys[i] = (key & 0xFFFFFFFF00000000ull) | (u64)(((uint32_t)y << 16) | (uint32_t)x);
-      const bool sup = (bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u;
+      const bool sup = have_bitmap && ((bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u);
       state[i] = sup ? ST_SUPP : ST_UNDEC;
       // d == 0: a point only suppresses its own pixel, nothing interacts
       if (!sup && d > 0) next[i] = (uint16_t)atomicExch(&head[(y >> 3) * Wc + (x >> 3)], i);
@@ -579,6 +583,11 @@ __global__ void __launch_bounds__(kDetectThreads, 1) k_detect(DetectParams p) {
 
     // ---- D: more candidates are needed: record this chunk's boxes, take the next `cap` keys --------
     slow = true;
+    if (!have_bitmap) {
+      for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
+      have_bitmap = true;
+      __syncthreads();
+    }
     for (int i = tid; i < n; i += kDetectThreads) {
       if (state[i] != ST_KEPT) continue;
       const uint32_t xy = (uint32_t)keys[i];
@@ -840,7 +849,8 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
 static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   const int ww = (W + 31) >> 5;
   const size_t cells = (size_t)(H / 8) * (W / 8);
-  return (size_t)cap * 8 + (size_t)K * 8 + (size_t)H * ww * 4 + cells * 4 + (size_t)cap * 2 + (size_t)cap * 2;
+  (void)ww;
+  return (size_t)cap * 8 + (size_t)K * 8 + cells * 4 + (size_t)cap * 2 + (size_t)cap * 2;
 }
 
 // One contiguous range of images [b0, b0 + B) on the handle's CURRENT stream (h->stream).
@@ -876,6 +886,8 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
     int4* kp_par = streaming ? h->kp_par + (size_t)b0 * K : nullptr;
     float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * K : nullptr;
     p.kp_par = kp_par;
+    p.bitmap = h->nms_bitmap + (size_t)b0 * ((size_t)h->max_h * h->max_w / 16 + 64);
+    p.bitmap_stride = (size_t)h->max_h * h->max_w / 16 + 64;
     p.cap = K <= 1536 ? 4096 : 8192;
     p.target = min(p.cap * 3 / 4, K + K / 2 + 256);
     const size_t smem = detect_smem_bytes(H, W, K, p.cap);

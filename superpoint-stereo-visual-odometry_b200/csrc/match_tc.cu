@@ -656,7 +656,7 @@ k_tc_fill_dist(const MatchProblem* __restrict__ probs, int mode, int max_rows, i
 // ------------------------------------------------------------------------------------------------
 constexpr int kFbRows = 8;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm, int cap,
               int max_rows, int max_cols, const int* __restrict__ fb_count, const int* __restrict__ fb_list,
               int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
@@ -691,7 +691,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
     }
     float v[3] = {INFINITY, INFINITY, INFINITY};
     int ix[3] = {-1, -1, -1};
-    constexpr int kU = 4;  // columns per step; the next step's loads are issued before this step's math
+    constexpr int kU = 2;  // columns per step; the next step's loads are issued before this step's math
     float4 xs[kU], ys[kU], xn[kU], yn[kU];
     float nbs[kU], nbn[kU];
     auto load_cols = [&](int jb, float4* x, float4* y, float* nb) {
