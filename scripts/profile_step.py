@@ -8,7 +8,7 @@ import torch
 import spvo_b200 as S
 import spvo_b200.synth as synth
 
-F = int(sys.argv[1]) if len(sys.argv) > 1 else 74
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 alg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 H, W, K = 376, 1240, 1000
