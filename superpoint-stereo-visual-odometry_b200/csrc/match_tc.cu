@@ -44,15 +44,19 @@
 namespace spvo {
 
 constexpr int kDim = SPVO_DESC_DIM;       // 256
-constexpr int kBM = 128, kBN = 128;       // CTA tile: 128 rows of A x 128 rows of B
-constexpr int kKB = 64;                   // k-block = one 128-byte swizzle atom of bf16
+constexpr int kBM = 128;                  // rows of one MMA block of A (tcgen05 M)
+constexpr int kABlocks = 2;               // A blocks resident per work item
+constexpr int kItemRows = kBM * kABlocks; // 256 rows of A per work item; operand slots are padded to this
+constexpr int kBN = 128;                  // columns (rows of B) per tile (tcgen05 N)
+constexpr int kKB = 64;                   // k-block = one 128-byte swizzle atom of 16-bit elements
 constexpr int kNumKB = kDim / kKB;        // 4
-constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) block
-constexpr int kStages = 2;
+constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) k-block of A or B = one TMA box
+constexpr int kBSlots = 5;                // B k-blocks in flight (ring)
+constexpr int kAccStages = 2;             // accumulator stages in TMEM
+constexpr int kTmemCols = kAccStages * kABlocks * kBN;  // 512: all of TMEM (one CTA per SM)
 constexpr int kTop = 3;
-constexpr int kEpiWarps = 8;              // 2 per TMEM lane quadrant: each owns 64 of a tile's 128 columns
+constexpr int kEpiWarps = 8;              // one per (A block, TMEM lane quadrant): 32 rows x the tile's 128 columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
-constexpr int kLists = 2;                 // shortlists per row (one per column half), merged by k_tc_rerank
 // |approx d^2 - exact d^2| <= eps_rel*|a||b| + kEpsAbs*(|a|^2+|b|^2):
 //   bf16 operands (any CV_32F input):        2*(2^-8  + 2^-18 + 2^-14) -> 0.0085
 //   fp16 operands (|x| <= 1, unit-norm rows): 2*(2^-10 + 2^-22 + 2^-14) -> 0.0022; fp16 subnormals (|x| < 2^-14) add
@@ -204,14 +208,23 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 
 // ------------------------------------------------------------------------------------------------
 // k_tc_gemm
+//
+// Tile shape.  The kernel streams B from L2 against an A block that stays in shared memory, so the
+// L2 -> SM traffic per output is 2 B * 256 / (resident A rows).  With 128 resident rows a 128 x 128 tile
+// costs 64 KB of TMA traffic per 1084 tensor-core cycles = 60 B/clk per SM, above the ~43 B/clk per SM the
+// L2 sustains chip-wide: the first version of this kernel was L2-bound at ~45% of tensor peak.  Keeping
+// 256 rows of A resident (two 128-row MMA blocks, 128 KB) halves that to 30 B/clk per SM.  The MMA shape
+// stays 128 x 128 x 16 (N = 64 instructions re-read the A operand from shared memory twice as often and
+// measured slower); the B operand therefore streams through a ring of 16 KB k-blocks (128 columns x 64 k),
+// each consumed by the 8 MMAs of both row blocks and then released.
 // ------------------------------------------------------------------------------------------------
-constexpr int kNormRing = 4;  // tile ct's column norms live in slot ct % 4 (see the producer for why 4 is safe)
+constexpr int kNormRing = 4;  // tile gt's column norms live in slot gt % 4 (see the producer for why 4 is safe)
 struct __align__(16) TcShared {
   float nrm[kNormRing][kBN];
-  uint64_t a_full, a_empty;
-  uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % 4
-  uint64_t b_full[kStages], b_empty[kStages];
-  uint64_t acc_full[kStages], acc_empty[kStages];
+  uint64_t a_full[kNumKB], a_empty;
+  uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % kNormRing
+  uint64_t b_full[kBSlots], b_empty[kBSlots];
+  uint64_t acc_full[kAccStages], acc_empty[kAccStages];
   uint32_t tmem_base;
 };
 
@@ -226,15 +239,23 @@ __device__ __forceinline__ void top3_net(uint32_t x, uint32_t& k0, uint32_t& k1,
   k2 = min(k2, x);
 }
 
+// One arrival per WARP: 256 per-thread arrivals on one mbarrier serialise (~8 clk each) and sat on the critical
+// path between "accumulator drained" and the next tile's first MMA.
+__device__ __forceinline__ void epi_release(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
   tmem_ld32(taddr, r);
   tmem_ld32(taddr + 32, r + 32);
 }
 
-// Work item = (directed problem dp, 128-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
-// items bid, bid + grid, ...; barriers and TMEM are set up once, and the B-tile / accumulator pipelines
-// run continuously across items (a global tile counter gives stage and phase), so only the A block
-// reload at an item boundary is exposed.
+// Work item = (directed problem dp, 256-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
+// items bid, bid + grid, ...; barriers and TMEM are set up once, and the B ring / accumulator pipelines
+// run continuously across items (global k-block and tile counters give slot and phase): the first B tile
+// of the next item is already in flight while the last MMAs of the current one retire, and the A reload
+// is consumed k-block by k-block as it lands.
 struct TcItem {
   int dp, rb, Na, Nb, a_op, b_op, nct;
   bool valid;
@@ -251,7 +272,7 @@ __device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs
   it.a_op = rev ? pr.b_op : pr.a_op;
   it.b_op = rev ? pr.a_op : pr.b_op;
   it.nct = (it.Nb + kBN - 1) / kBN;
-  it.valid = it.rb * kBM < it.Na;
+  it.valid = it.rb * kItemRows < it.Na && it.nct > 0;
   return it;
 }
 
@@ -260,30 +281,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
           int cap, uint32_t idesc, uint32_t idx_mask, int n_items) {
   extern __shared__ uint8_t smem_raw[];
-  const int nrb = cap / kBM;
+  const int nrb = cap / kItemRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // carve shared memory: operands need 1024 B alignment for the 128 B swizzle
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;                                    // 4 x 16 KB
-  const uint32_t sB = base + kNumKB * kTileBytes;              // kStages x 4 x 16 KB
-  TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (sB + kStages * kNumKB * kTileBytes - smem_u32(smem_raw)));
+  const uint32_t sA = base;                                  // [kABlocks][4 k-blocks] x 16 KB
+  const uint32_t sB = base + kABlocks * kNumKB * kTileBytes;  // ring of kBSlots x 16 KB k-blocks
+  TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (sB + kBSlots * kTileBytes - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&sh->a_full), 1);
+    for (int kb = 0; kb < kNumKB; ++kb) mbar_init(smem_u32(&sh->a_full[kb]), 1);
     mbar_init(smem_u32(&sh->a_empty), 1);
     for (int s = 0; s < kNormRing; ++s) mbar_init(smem_u32(&sh->nrm_full[s]), 1);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kBSlots; ++s) {
       mbar_init(smem_u32(&sh->b_full[s]), 1);
       mbar_init(smem_u32(&sh->b_empty[s]), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
       mbar_init(smem_u32(&sh->acc_full[s]), 1);
-      mbar_init(smem_u32(&sh->acc_empty[s]), 32 * kEpiWarps);
+      mbar_init(smem_u32(&sh->acc_empty[s]), kEpiWarps);  // one elected arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 2 accumulator stages x 128 fp32 columns
+  if (warp == 1) {  // TMEM (all 512 columns): 2 accumulator stages x 2 row blocks x 128 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(kStages * kBN)
+                 "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -295,110 +318,132 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   if (warp == 0) {
     // ===== TMA producer (one elected lane) =====
     if (lane == 0) {
-      uint32_t gt = 0, ai = 0;  // global tile counter, count of items that loaded an A block
+      uint32_t gt = 0, gk = 0, ai = 0;  // global tile / k-block counters, count of items that loaded A
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const TcItem it = tc_item(probs, P, w, nrb);
-        if (!it.valid || it.nct == 0) continue;
-        mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A block
-        const int a_row = it.a_op * cap + it.rb * kBM;
-        mbar_expect_tx(smem_u32(&sh->a_full), kNumKB * kTileBytes);
-        for (int kb = 0; kb < kNumKB; ++kb)
-          tma_load_2d(sA + kb * kTileBytes, &tmap, smem_u32(&sh->a_full), kb * kKB, a_row);
-        ++ai;
+        if (!it.valid) continue;
+        auto load_a = [&]() {
+          mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A blocks
+          ++ai;
+          const int a_row = it.a_op * cap + it.rb * kItemRows;
+          for (int kb = 0; kb < kNumKB; ++kb) {
+            mbar_expect_tx(smem_u32(&sh->a_full[kb]), kABlocks * kTileBytes);
+            for (int b = 0; b < kABlocks; ++b)
+              tma_load_2d(sA + (b * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->a_full[kb]), kb * kKB,
+                          a_row + b * kBM);
+          }
+        };
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
-          const int s = gt % kStages, ph = (gt / kStages) & 1;
-          mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
-          mbar_expect_tx(smem_u32(&sh->b_full[s]), kNumKB * kTileBytes);
+          // A is requested AFTER the item's first B tile: that tile only needs free ring slots, so it is in
+          // flight while the previous item's last MMAs (which still read the A blocks) retire
+          if (ct == 1) load_a();
           const int b_row = it.b_op * cap + ct * kBN;
-          for (int kb = 0; kb < kNumKB; ++kb)
-            tma_load_2d(sB + (s * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
-          // the tile's 128 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits on
-          // it directly).  The slot is rewritten by tile gt+4, whose load waits for the MMAs of tile gt+2, which
-          // waited for the epilogue to drain tile gt (norms already in registers): no overwrite race.
+          // the tile's 128 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits
+          // on it directly).  The slot is rewritten by tile gt+4, whose first k-block reuses a ring slot last
+          // read by the MMAs of tile gt+2, which waited for the epilogue to drain tile gt (norms already in
+          // registers): no overwrite race.
           const uint32_t nb_bar = smem_u32(&sh->nrm_full[gt % kNormRing]);
-          mbar_expect_tx(nb_bar, kBN * 4);
-          bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, nb_bar);
+          for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
+            const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
+            mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
+            mbar_expect_tx(smem_u32(&sh->b_full[s]), kTileBytes);
+            tma_load_2d(sB + s * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
+            if (kb == 0) {
+              mbar_expect_tx(nb_bar, kBN * 4);
+              bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, nb_bar);
+            }
+          }
+          if (it.nct == 1) load_a();
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
-      uint32_t gt = 0, ai = 0;
+      uint32_t gt = 0, gk = 0, ai = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const TcItem it = tc_item(probs, P, w, nrb);
-        if (!it.valid || it.nct == 0) continue;
-        mbar_wait(smem_u32(&sh->a_full), ai & 1);
-        ++ai;
+        if (!it.valid) continue;
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
-          const int s = gt % kStages, ph = (gt / kStages) & 1;
-          mbar_wait(smem_u32(&sh->acc_empty[s]), ph ^ 1);  // epilogue drained this accumulator
-          mbar_wait(smem_u32(&sh->b_full[s]), ph);         // TMA landed this B stage
-          tc_fence_after();
-          const uint32_t d = tmem_base + s * kBN;
+          const int sa = gt % kAccStages, pha = (gt / kAccStages) & 1;
+          mbar_wait(smem_u32(&sh->acc_empty[sa]), pha ^ 1);  // epilogue drained this accumulator stage
 #pragma unroll
-          for (int kb = 0; kb < kNumKB; ++kb) {
+          for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
+            const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
+            if (ct == 0) mbar_wait(smem_u32(&sh->a_full[kb]), ai & 1);  // this k-slice of both A blocks landed
+            mbar_wait(smem_u32(&sh->b_full[s]), ph);                    // TMA landed this B k-block
+            tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < kKB / 16; ++k) {
-              const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
-              const uint64_t bd = umma_desc_sw128(sB + (s * kNumKB + kb) * kTileBytes + k * 32);
-              tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
+            for (int b = 0; b < kABlocks; ++b) {
+              const uint32_t d = tmem_base + (sa * kABlocks + b) * kBN;
+#pragma unroll
+              for (int k = 0; k < kKB / 16; ++k) {
+                const uint64_t ad = umma_desc_sw128(sA + (b * kNumKB + kb) * kTileBytes + k * 32);
+                const uint64_t bd = umma_desc_sw128(sB + s * kTileBytes + k * 32);
+                tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
+              }
             }
+            tc_commit(smem_u32(&sh->b_empty[s]));  // ring slot free once these 8 MMAs retire
           }
-          tc_commit(smem_u32(&sh->b_empty[s]));   // smem stage free once these MMAs retire
-          tc_commit(smem_u32(&sh->acc_full[s]));  // accumulator ready for the epilogue
+          tc_commit(smem_u32(&sh->acc_full[sa]));  // both accumulators ready for the epilogue
         }
-        tc_commit(smem_u32(&sh->a_empty));  // A block free once the item's last MMAs retire
+        ++ai;
+        tc_commit(smem_u32(&sh->a_empty));  // A blocks free once the item's last MMAs retire
       }
     }
   } else {
-    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; column half = (warp - 2) / 4 =====
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; A row block = (warp - 2) / 4 =====
+    const int quad = warp & 3, blk = (warp - 2) >> 2;
     uint32_t gt = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const TcItem it = tc_item(probs, P, w, nrb);
       if (!it.valid) continue;
-      const int row = it.rb * kBM + quad * 32 + lane;
+      const int row = it.rb * kItemRows + blk * kBM + quad * 32 + lane;
       uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
       const float off = key_offset(__uint_as_float(opmax[it.a_op]), __uint_as_float(opmax[it.b_op]));
+      const uint32_t nmask = ~idx_mask;
       for (int ct = 0; ct < it.nct; ++ct, ++gt) {
-        const int s = gt % kStages, ph = (gt / kStages) & 1;
-        const int j0 = ct * kBN + half * 64;
-        mbar_wait(smem_u32(&sh->acc_full[s]), ph);
+        const int sa = gt % kAccStages, pha = (gt / kAccStages) & 1;
+        mbar_wait(smem_u32(&sh->acc_full[sa]), pha);
         tc_fence_after();
-        uint32_t acc[64];
-        tmem_ld64(tmem_base + s * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
         // the tile's column norms were bulk-copied to shared memory next to its B operand (broadcast LDS.128)
         mbar_wait(smem_u32(&sh->nrm_full[gt % kNormRing]), (gt / kNormRing) & 1);
-        float4 n4[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][half * 64 + 4 * e]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&sh->acc_empty[s]));  // accumulator is in registers: release it to the MMA warp
-        // tile-local shortlist first: the column-in-tile index is an immediate of the packing LOP3 (one ALU op
-        // per element instead of add + LOP3); the three survivors get the tile's column base OR-ed in afterwards
-        uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu, l2 = 0xFFFFFFFFu;
-        const uint32_t nmask = ~idx_mask;
+        for (int half = 0; half < 2; ++half) {
+          const int j0 = ct * kBN + half * 64;
+          uint32_t acc[64];
+          tmem_ld64(tmem_base + (sa * kABlocks + blk) * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
+          float4 n4[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
-            const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
-            const uint32_t key = (__float_as_uint(g) & nmask) | (uint32_t)(4 * e + u);
-            top3_net(key, l0, l1, l2);
+          for (int e = 0; e < 16; ++e)
+            n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][half * 64 + 4 * e]);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            epi_release(smem_u32(&sh->acc_empty[sa]), lane);  // accumulator is in registers: release it to the MMA warp
           }
+          // tile-local shortlist first: the column-in-tile index is an immediate of the packing LOP3 (one ALU op
+          // per element instead of add + LOP3); the three survivors get the column base OR-ed in afterwards
+          uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu, l2 = 0xFFFFFFFFu;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
+              const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
+              const uint32_t key = (__float_as_uint(g) & nmask) | (uint32_t)(4 * e + u);
+              top3_net(key, l0, l1, l2);
+            }
+          }
+          // j0 is a multiple of 64 and the local index < 64, so OR == add; 0xFFFFFFFF (empty) stays the maximum
+          top3_net(l0 | (uint32_t)j0, k0, k1, k2);
+          top3_net(l1 | (uint32_t)j0, k0, k1, k2);
+          top3_net(l2 | (uint32_t)j0, k0, k1, k2);
         }
-        // j0 is a multiple of 64 and the local index < 64, so OR == add; 0xFFFFFFFF (empty) stays the maximum
-        top3_net(l0 | (uint32_t)j0, k0, k1, k2);
-        top3_net(l1 | (uint32_t)j0, k0, k1, k2);
-        top3_net(l2 | (uint32_t)j0, k0, k1, k2);
       }
       if (row < it.Na) {
-        uint32_t* o = top_key + (((size_t)it.dp * cap + row) * kLists + half) * kTop;
+        uint32_t* o = top_key + ((size_t)it.dp * cap + row) * kTop;
         o[0] = k0;
         o[1] = k1;
         o[2] = k2;
@@ -409,7 +454,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kStages * kBN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -437,10 +482,10 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
   if (Nb == 0) {
     resolved = true;
   } else if (Nb > kTop && !(mode == SPVO_MATCH_KNN_RATIO && !rev)) {
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kTop;
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    for (int e = 0; e < kTop; ++e) top3_net(kp[e], k0, k1, k2);
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const float off = key_offset(amax, bmax);
@@ -525,10 +570,10 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   (void)Na;
   if (Nb > 0) {
     // merge the two per-half shortlists: the kTop smallest packed keys of the row
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kTop;
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    for (int e = 0; e < kTop; ++e) top3_net(kp[e], k0, k1, k2);
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const float off = key_offset(amax, bmax);
@@ -901,7 +946,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
     if ((e = cudaMalloc((void**)&w->rr_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_count, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
     w->top_rows = top_rows;
   }
   return cudaSuccess;
@@ -929,7 +974,7 @@ static cudaError_t tc_get(Handle* h, TcWorkspace** w, size_t ops, size_t cap, si
 
 cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink) {
   TcWorkspace* w;
-  const int cap = (max_rows + kBM - 1) / kBM * kBM;
+  const int cap = (max_rows + kItemRows - 1) / kItemRows * kItemRows;
   cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir);
   if (e != cudaSuccess) return e;
   w->slot_cap = cap;
@@ -972,7 +1017,7 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
   if ((e = ensure_select_buffers(h, P, mr, mc)) != cudaSuccess) return e;
   if (max_rows > 0 && max_cols > 0) {
     const int mx = max_rows > max_cols ? max_rows : max_cols;
-    int cap = (mx + kBM - 1) / kBM * kBM;
+    int cap = (mx + kItemRows - 1) / kItemRows * kItemRows;
     const bool cross = cfg.mode == SPVO_MATCH_NN_CROSSCHECK;
     const int ndir = cross ? 2 * P : P;
     TcWorkspace* w;
@@ -997,11 +1042,11 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     const uint32_t idx_mask = (1u << idx_bits) - 1u;
     const float key_rel = 1.0f / (float)(1u << (23 - idx_bits));
     const float eps_rel = w->fp16 ? kEpsRelFp16 : kEpsRelBf16;
-    const size_t smem = 1024 + (size_t)(1 + kStages) * kNumKB * kTileBytes + sizeof(TcShared);
+    const size_t smem = 1024 + (size_t)(kABlocks * kNumKB + kBSlots) * kTileBytes + sizeof(TcShared);
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_GEMM);
-      const int n_items = (cap / kBM) * ndir;
+      const int n_items = (cap / kItemRows) * ndir;
       const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
       k_tc_gemm<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
                                                 make_idesc(w->fp16), idx_mask, n_items);
