@@ -758,10 +758,23 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
     if (threadIdx.x < cells - tail0) cp_async4(dst + (tail0 + threadIdx.x) * 4, src + tail0 + threadIdx.x);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // the sampling parameters of this thread's keypoints travel while the planes are in flight
+  constexpr int kPre = 4;
+  int4 pre[kPre];
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    const int k = threadIdx.x + 256 * i;
+    pre[i] = k < n ? __ldg(kp_par + (size_t)b * K + k) : make_int4(0, 0, 0, 0);
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  for (int k = threadIdx.x; k < n; k += 256) {
-    const int4 par = kp_par[(size_t)b * K + k];
+#pragma unroll 1
+  for (int k0 = 0; k0 < n; k0 += 256 * kPre) {
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    const int k = k0 + threadIdx.x + 256 * i;
+    if (k >= n) break;
+    const int4 par = k0 == 0 ? pre[i] : __ldg(kp_par + (size_t)b * K + k);
     const int o_tl = par.x, dr = par.y & 0x3FFFFFFF, dc = (par.y >> 30) & 1;
     const float rr = __int_as_float(par.z), cr = __int_as_float(par.w);
     const float irr = __fsub_rn(1.0f, rr), icr = __fsub_rn(1.0f, cr);
@@ -774,6 +787,7 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
       const float t4 = __fmul_rn(__fmul_rn(pl[o_tl + dr + dc], irr), icr);
       tmp[((size_t)b * 256 + (size_t)cg * kCP + c) * K + k] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
     }
+  }
   }
 }
 

@@ -210,13 +210,17 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 // k_tc_gemm
 //
 // Tile shape.  The kernel streams B from L2 against an A block that stays in shared memory, so the
-// L2 -> SM traffic per output is 2 B * 256 / (resident A rows).  With 128 resident rows a 128 x 128 tile
-// costs 64 KB of TMA traffic per 1084 tensor-core cycles = 60 B/clk per SM, above the ~43 B/clk per SM the
-// L2 sustains chip-wide: the first version of this kernel was L2-bound at ~45% of tensor peak.  Keeping
-// 256 rows of A resident (two 128-row MMA blocks, 128 KB) halves that to 30 B/clk per SM.  The MMA shape
-// stays 128 x 128 x 16 (N = 64 instructions re-read the A operand from shared memory twice as often and
-// measured slower); the B operand therefore streams through a ring of 16 KB k-blocks (128 columns x 64 k),
-// each consumed by the 8 MMAs of both row blocks and then released.
+// L2 -> SM traffic per output is 2 B * 256 / (resident A rows).  256 rows of A are resident (two 128-row
+// MMA blocks, 128 KB): 30 B/clk per SM, below the ~43 B/clk per SM the L2 sustains chip-wide.  The MMA
+// shape stays 128 x 128 x 16 (N = 64 instructions measured 1.5x slower per output), so the B operand
+// streams through a ring of 16 KB k-blocks (128 columns x 64 k), each consumed by the 8 MMAs of both row
+// blocks and then released.
+//
+// What bounds it (B200, 148 pairs per launch, parts of the kernel switched off one at a time):
+// with the epilogue reduced to "wait, release" the MMA side alone takes 0.23 ms = 1.5 PFLOP/s, the rate
+// cuBLAS bf16 reaches on the same GPU (MEASURED_PEAKS.json: 1.36 sustained .. 1.63 burst); removing every
+// B load changes that by < 3 %, the TMEM read-out by < 1 %, and taking the A operand from tensor memory
+// (TS form) does not help either.  The top-3 network (8 instructions per output) adds 0.08 ms on top.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNormRing = 4;  // tile gt's column norms live in slot gt % 4 (see the producer for why 4 is safe)
 struct __align__(16) TcShared {
