@@ -111,7 +111,7 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   ALLOC(h->st_desc_out, (size_t)max_batch * K * 256 * sizeof(float));
   ALLOC(h->st_n, (size_t)max_batch * sizeof(int));
   ALLOC(h->st_scores, (size_t)max_batch * K * sizeof(float));
-  ALLOC(h->desc_tmp, (size_t)max_batch * 256 * K * sizeof(float));
+  ALLOC(h->desc_tmp, (size_t)max_batch * 256 * ((K + 3) & ~3) * sizeof(float));
   ALLOC(h->kp_par, (size_t)max_batch * K * sizeof(int4));
   ALLOC(h->probs, 4096 * sizeof(MatchProblem));
   h->probs_cap = 4096;

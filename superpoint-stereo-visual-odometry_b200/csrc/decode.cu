@@ -737,7 +737,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 __global__ void __launch_bounds__(256)
 k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, const int* __restrict__ n_out,
-              float* __restrict__ tmp, int cells, int K, int plane_pitch) {
+              float* __restrict__ tmp, int cells, int K, int plane_pitch, int Kp) {
   extern __shared__ __align__(16) float sp[];  // kCP planes, each plane_pitch floats
   const int b = blockIdx.y, cg = blockIdx.x;
   const int n = n_out[b];
@@ -785,7 +785,7 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
       const float t2 = __fmul_rn(__fmul_rn(pl[o_tl + dc], rr), icr);
       const float t3 = __fmul_rn(__fmul_rn(pl[o_tl + dr], irr), cr);
       const float t4 = __fmul_rn(__fmul_rn(pl[o_tl + dr + dc], irr), icr);
-      tmp[((size_t)b * 256 + (size_t)cg * kCP + c) * K + k] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
+      tmp[((size_t)b * 256 + (size_t)cg * kCP + c) * Kp + k] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
     }
   }
   }
@@ -793,17 +793,30 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
 
 // 32 keypoints per block: [256][K] scratch -> shared [32][257] -> normalised [K][256] rows.
 __global__ void __launch_bounds__(256)
-k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K,
+k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K, int Kp,
                  TcSink sink) {
   __shared__ float s[32][257];
   const int b = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = n_out[b];
   if (k0 < n) {
-    const float* src = tmp + (size_t)b * 256 * K;
-    if (k0 + lane < n) {
-#pragma unroll 8
-      for (int c = w; c < 256; c += 8) s[lane][c] = __ldg(src + (size_t)c * K + k0 + lane);
+    // 16-byte loads: thread (c_sub = t / 8, j = t % 8) takes keypoints k0 + 4j .. + 3 of channels c_sub + 32 i; all 8
+    // loads are in flight at once (the scratch pitch Kp is a multiple of 4).  The scattered shared stores hit banks
+    // (4j + q + c) % 32: conflict-free.
+    const float* src = tmp + (size_t)b * 256 * Kp + k0;
+    const int j = threadIdx.x & 7, cs = threadIdx.x >> 3;
+    if (k0 + 4 * j < n) {
+      float4 q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(cs + 32 * i) * Kp) + j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cs + 32 * i;
+        s[4 * j + 0][c] = q[i].x;
+        s[4 * j + 1][c] = q[i].y;
+        s[4 * j + 2][c] = q[i].z;
+        s[4 * j + 3][c] = q[i].w;
+      }
     }
   }
   __syncthreads();
@@ -898,7 +911,8 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
     const size_t smem_planes = (size_t)kCP * plane_pitch * sizeof(float);
     const bool streaming = desc && desc_out && h->desc_tmp && h->kp_par && smem_planes <= 200 * 1024;
     int4* kp_par = streaming ? h->kp_par + (size_t)b0 * K : nullptr;
-    float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * K : nullptr;
+    const int Kp = (K + 3) & ~3;  // scratch pitch: 16-byte loads in k_desc_normalize
+    float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * Kp : nullptr;
     p.kp_par = kp_par;
     p.bitmap = h->nms_bitmap + (size_t)b0 * ((size_t)h->max_h * h->max_w / 16 + 64);
     p.bitmap_stride = (size_t)h->max_h * h->max_w / 16 + 64;
@@ -934,7 +948,7 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
           LaunchScope ls(h, KID_DESC_PLANES);
           k_desc_planes<<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(desc + (size_t)g0 * 256 * cells,
                                                                        kp_par + (size_t)g0 * K, n_out + g0,
-                                                                       tmp + (size_t)g0 * 256 * K, cells, K, plane_pitch);
+                                                                       tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
         }
         TcSink sg = sk;
         if (sg.xb) {
@@ -943,8 +957,8 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
           sg.opmax += g0;
         }
         LaunchScope ls(h, KID_DESC_NORM);
-        k_desc_normalize<<<dim3((rows + 31) / 32, gb), 256, 0, st>>>(tmp + (size_t)g0 * 256 * K, n_out + g0,
-                                                                    desc_out + (size_t)g0 * K * 256, K, sg);
+        k_desc_normalize<<<dim3((rows + 31) / 32, gb), 256, 0, st>>>(tmp + (size_t)g0 * 256 * Kp, n_out + g0,
+                                                                    desc_out + (size_t)g0 * K * 256, K, Kp, sg);
       }
     } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);
