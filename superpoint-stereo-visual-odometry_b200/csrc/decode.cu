@@ -22,81 +22,63 @@
 namespace spvo {
 
 // ------------------------------------------------------------------------------------------------
-// K1: softmax + heatmap.  Block = 256 threads = 32 consecutive cells x 8 heatmap rows.
-//   thread (grp = warp id, lane): cell = 32*blockIdx.x + lane, channels 8*grp .. 8*grp+7
-//   -> every global load is one 128 B coalesced request per warp (channel plane, consecutive cells)
-//   -> every warp stores 32 cells x 32 B = 1 KB contiguous of heatmap row 8*hc + grp.
-// The 65-term channel sum must be accumulated in channel order (oracle: s = s + e_c, c = 0..64), so
-// the exps go through shared memory and warp 0 does the ordered sum for the block's 32 cells.
+// K1: softmax + heatmap.  One THREAD per 8x8 cell, 128 consecutive cells per block.
+//   * every global load is one 128 B coalesced request per warp (a channel plane, 32 consecutive cells); all 65
+//     loads of a thread are independent, so a warp keeps up to 8 KB in flight;
+//   * the 65-term channel sum must be accumulated in channel order (oracle: s = s + e_c, c = 0..64): it is a
+//     plain sequential chain inside the thread -- no shared memory, no barriers;
+//   * channel c is pixel (c / 8, c % 8) of the cell: per heatmap row a warp stores 32 cells x 32 B = 1 KB
+//     contiguous.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kHeatThreads = 128;
+__global__ void __launch_bounds__(kHeatThreads, 4)
 k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
                float* __restrict__ cellmax, int Hc, int Wc, float conf) {
-  __shared__ float e_s[65][32];
-  __shared__ float denom_s[32];
-  __shared__ float rowmax_s[8][32];
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int cell = blockIdx.x * 32 + lane;
-  const bool valid = cell < cells;
+  const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
+  if (cell >= cells) return;
   const float* src = semi + (size_t)b * 65 * cells + cell;
-  float e[8];
-  if (valid) {
-    float xin[8];
+  float e[64];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xin[j] = __ldg(src + (size_t)(8 * grp + j) * cells);
-    float xd = 0.f;
-    if (grp == 1) xd = __ldg(src + (size_t)64 * cells);
+  for (int c = 0; c < 64; ++c) e[c] = __ldg(src + (size_t)c * cells);
+  const float xd = __ldg(src + (size_t)64 * cells);
+  float s = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      e[j] = spvo_exp(xin[j]);
-      e_s[8 * grp + j][lane] = e[j];
-    }
-    if (grp == 1) e_s[64][lane] = spvo_exp(xd);
+  for (int c = 0; c < 64; ++c) {
+    e[c] = spvo_exp(e[c]);
+    s = __fadd_rn(s, e[c]);
   }
-  __syncthreads();
-  if (grp == 0 && valid) {
-    float s = 0.0f;
-#pragma unroll 13
-    for (int c = 0; c < 65; ++c) s = __fadd_rn(s, e_s[c][lane]);
-    denom_s[lane] = __fadd_rn(s, 0.00001f);
-  }
-  __syncthreads();
-  float p[8], pm = 0.0f;
-  if (valid) {
-    const float denom = denom_s[lane];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      p[j] = __fdiv_rn(e[j], denom);
-      pm = fmaxf(pm, p[j]);
-    }
-  }
-  rowmax_s[grp][lane] = pm;
-  __syncthreads();
-  if (!valid) return;
-  if (grp == 0) {  // per-cell maximum: lets k_detect skip cells that cannot hold a first-chunk candidate
-    float cm = pm;
-#pragma unroll
-    for (int g = 1; g < 8; ++g) cm = fmaxf(cm, rowmax_s[g][lane]);
-    cellmax[(size_t)b * cells + cell] = cm;
-  }
+  s = __fadd_rn(s, spvo_exp(xd));
+  const float denom = __fadd_rn(s, 0.00001f);
   const int hc = cell / Wc, wc = cell - hc * Wc;
   const int W = Wc * 8;
-  float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc + grp) * W + 8 * wc;
-  reinterpret_cast<float4*>(dst)[0] = make_float4(p[0], p[1], p[2], p[3]);
-  reinterpret_cast<float4*>(dst)[1] = make_float4(p[4], p[5], p[6], p[7]);
-  // Sampled histogram: one pixel per (cell, row) on a diagonal -> 8 of the cell's 64 pixels.
-  // Only used to ESTIMATE the first chunk's score threshold; exactness never depends on it.
-  const int js = (grp + cell) & 7;
-  float v = p[0];
+  float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc) * W + 8 * wc;
+  float cm = 0.0f;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) v = (j == js) ? p[j] : v;
-  if (v > conf) {
-    uint32_t bits = fbits(v);
-    uint32_t bin = bits >= kOneBits ? 0u : min((kOneBits - bits) >> kHistShift, (uint32_t)(kHistBins - 1));
-    atomicAdd(&hist[(size_t)b * kHistBins + bin], 1u);
+  for (int r = 0; r < 8; ++r) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p[j] = __fdiv_rn(e[8 * r + j], denom);
+      cm = fmaxf(cm, p[j]);
+    }
+    reinterpret_cast<float4*>(dst + (size_t)r * W)[0] = make_float4(p[0], p[1], p[2], p[3]);
+    reinterpret_cast<float4*>(dst + (size_t)r * W)[1] = make_float4(p[4], p[5], p[6], p[7]);
+    // Sampled histogram: one pixel per (cell, row) on a diagonal -> 8 of the cell's 64 pixels.
+    // Only used to ESTIMATE the first chunk's score threshold; exactness never depends on it.
+    const int js = (r + cell) & 7;
+    float v = p[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) v = (j == js) ? p[j] : v;
+    if (v > conf) {
+      uint32_t bits = fbits(v);
+      uint32_t bin = bits >= kOneBits ? 0u : min((kOneBits - bits) >> kHistShift, (uint32_t)(kHistBins - 1));
+      atomicAdd(&hist[(size_t)b * kHistBins + bin], 1u);
+    }
   }
+  // per-cell maximum: lets k_detect skip cells that cannot hold a first-chunk candidate
+  cellmax[(size_t)b * cells + cell] = cm;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -897,10 +879,10 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
   unsigned* hist = h->hist + (size_t)b0 * kHistBins;
   float* cellmax = h->cellmax + (size_t)b0 * cells;
   if ((e = cudaMemsetAsync(hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
-  dim3 g1((cells + 31) / 32, B);
+  dim3 g1((cells + kHeatThreads - 1) / kHeatThreads, B);
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
-    k_softmax_heat<<<g1, 256, 0, st>>>(semi, heat, hist, cellmax, Hc, Wc, cfg.conf_thresh);
+    k_softmax_heat<<<g1, kHeatThreads, 0, st>>>(semi, heat, hist, cellmax, Hc, Wc, cfg.conf_thresh);
   }
   if (K > 0) {
     DetectParams p;
