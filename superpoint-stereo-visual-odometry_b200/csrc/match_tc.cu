@@ -44,18 +44,19 @@
 namespace spvo {
 
 constexpr int kDim = SPVO_DESC_DIM;       // 256
-constexpr int kBM = 128;                  // rows of one MMA block of A (tcgen05 M)
-constexpr int kABlocks = 2;               // A blocks resident per work item
-constexpr int kItemRows = kBM * kABlocks; // 256 rows of A per work item; operand slots are padded to this
-constexpr int kBN = 128;                  // columns (rows of B) per tile (tcgen05 N)
+constexpr int kBM = 128;                  // rows of A per work item = tcgen05 M
+constexpr int kBN = 256;                  // columns (rows of B) per tile = tcgen05 N (the largest the instruction takes)
+constexpr int kCapAlign = 256;            // operand slots are padded to whole B tiles
 constexpr int kKB = 64;                   // k-block = one 128-byte swizzle atom of 16-bit elements
 constexpr int kNumKB = kDim / kKB;        // 4
-constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) k-block of A or B = one TMA box
-constexpr int kBSlots = 5;                // B k-blocks in flight (ring)
+constexpr int kTileBytes = kBM * kKB * 2; // 16 KB per (128 rows x 64 k) box = one TMA load
+constexpr int kBSlotBytes = kBN * kKB * 2; // 32 KB per B k-block (256 columns x 64 k) = two boxes
+constexpr int kBSlots = 4;                // B k-blocks in flight (ring) = one whole tile ahead
 constexpr int kAccStages = 2;             // accumulator stages in TMEM
-constexpr int kTmemCols = kAccStages * kABlocks * kBN;  // 512: all of TMEM (one CTA per SM)
+constexpr int kTmemCols = kAccStages * kBN;  // 512: all of TMEM (one CTA per SM)
+constexpr int kLists = 2;                 // shortlists per row (one per 128-column half of a tile), merged by triage / rerank
 constexpr int kTop = 3;
-constexpr int kEpiWarps = 8;              // one per (A block, TMEM lane quadrant): 32 rows x the tile's 128 columns
+constexpr int kEpiWarps = 8;              // one per (TMEM lane quadrant, 128-column half of the tile)
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
 // |approx d^2 - exact d^2| <= eps_rel*|a||b| + kEpsAbs*(|a|^2+|b|^2):
 //   bf16 operands (any CV_32F input):        2*(2^-8  + 2^-18 + 2^-14) -> 0.0085
@@ -209,18 +210,12 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 // ------------------------------------------------------------------------------------------------
 // k_tc_gemm
 //
-// Tile shape.  The kernel streams B from L2 against an A block that stays in shared memory, so the
-// L2 -> SM traffic per output is 2 B * 256 / (resident A rows).  256 rows of A are resident (two 128-row
-// MMA blocks, 128 KB): 30 B/clk per SM, below the ~43 B/clk per SM the L2 sustains chip-wide.  The MMA
-// shape stays 128 x 128 x 16 (N = 64 instructions measured 1.5x slower per output), so the B operand
-// streams through a ring of 16 KB k-blocks (128 columns x 64 k), each consumed by the 8 MMAs of both row
-// blocks and then released.
-//
-// What bounds it (B200, 148 pairs per launch, parts of the kernel switched off one at a time):
-// with the epilogue reduced to "wait, release" the MMA side alone takes 0.23 ms = 1.5 PFLOP/s, the rate
-// cuBLAS bf16 reaches on the same GPU (MEASURED_PEAKS.json: 1.36 sustained .. 1.63 burst); removing every
-// B load changes that by < 3 %, the TMEM read-out by < 1 %, and taking the A operand from tensor memory
-// (TS form) does not help either.  The top-3 network (8 instructions per output) adds 0.08 ms on top.
+// Tile shape: 128 rows of A resident in shared memory per work item, B streamed in 256-column tiles, one
+// tcgen05.mma = 128 x 256 x 16.  scripts/mma_microbench.cu (B200, all SMs issuing back to back from shared
+// memory): a 128 x 128 x 16 MMA costs ~165 clk, a 128 x 256 x 16 one ~210 clk -- the instruction has a large
+// fixed cost, so N = 256 does 1.6x the flops per clock; cuBLAS bf16 on the same GPU sustains 1.36-1.63 PFLOP/s
+// (MEASURED_PEAKS.json).  B moves as a ring of four 32 KB k-blocks (256 columns x 64 k, two TMA boxes), i.e.
+// one whole tile ahead of the MMAs; the two 256-column fp32 accumulators fill TMEM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNormRing = 4;  // tile gt's column norms live in slot gt % 4 (see the producer for why 4 is safe)
 struct __align__(16) TcShared {
@@ -243,8 +238,7 @@ __device__ __forceinline__ void top3_net(uint32_t x, uint32_t& k0, uint32_t& k1,
   k2 = min(k2, x);
 }
 
-// One arrival per WARP: 256 per-thread arrivals on one mbarrier serialise (~8 clk each) and sat on the critical
-// path between "accumulator drained" and the next tile's first MMA.
+// One arrival per WARP: 256 per-thread arrivals on one mbarrier serialise.
 __device__ __forceinline__ void epi_release(uint32_t bar, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
@@ -255,7 +249,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
   tmem_ld32(taddr + 32, r + 32);
 }
 
-// Work item = (directed problem dp, 256-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
+// Work item = (directed problem dp, 128-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
 // items bid, bid + grid, ...; barriers and TMEM are set up once, and the B ring / accumulator pipelines
 // run continuously across items (global k-block and tile counters give slot and phase): the first B tile
 // of the next item is already in flight while the last MMAs of the current one retire, and the A reload
@@ -276,7 +270,7 @@ __device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs
   it.a_op = rev ? pr.b_op : pr.a_op;
   it.b_op = rev ? pr.a_op : pr.b_op;
   it.nct = (it.Nb + kBN - 1) / kBN;
-  it.valid = it.rb * kItemRows < it.Na && it.nct > 0;
+  it.valid = it.rb * kBM < it.Na && it.nct > 0;
   return it;
 }
 
@@ -285,14 +279,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
           int cap, uint32_t idesc, uint32_t idx_mask, int n_items) {
   extern __shared__ uint8_t smem_raw[];
-  const int nrb = cap / kItemRows;
+  const int nrb = cap / kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // carve shared memory: operands need 1024 B alignment for the 128 B swizzle
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;                                  // [kABlocks][4 k-blocks] x 16 KB
-  const uint32_t sB = base + kABlocks * kNumKB * kTileBytes;  // ring of kBSlots x 16 KB k-blocks
-  TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (sB + kBSlots * kTileBytes - smem_u32(smem_raw)));
+  const uint32_t sA = base;                        // 4 k-blocks x 16 KB
+  const uint32_t sB = base + kNumKB * kTileBytes;  // ring of kBSlots x 32 KB k-blocks
+  TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (sB + kBSlots * kBSlotBytes - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < kNumKB; ++kb) mbar_init(smem_u32(&sh->a_full[kb]), 1);
@@ -308,7 +302,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM (all 512 columns): 2 accumulator stages x 2 row blocks x 128 fp32 columns
+  if (warp == 1) {  // TMEM (all 512 columns): 2 accumulator stages x 256 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"(kTmemCols)
                  : "memory");
@@ -327,31 +321,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         const TcItem it = tc_item(probs, P, w, nrb);
         if (!it.valid) continue;
         auto load_a = [&]() {
-          mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A blocks
+          mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A block
           ++ai;
-          const int a_row = it.a_op * cap + it.rb * kItemRows;
+          const int a_row = it.a_op * cap + it.rb * kBM;
           for (int kb = 0; kb < kNumKB; ++kb) {
-            mbar_expect_tx(smem_u32(&sh->a_full[kb]), kABlocks * kTileBytes);
-            for (int b = 0; b < kABlocks; ++b)
-              tma_load_2d(sA + (b * kNumKB + kb) * kTileBytes, &tmap, smem_u32(&sh->a_full[kb]), kb * kKB,
-                          a_row + b * kBM);
+            mbar_expect_tx(smem_u32(&sh->a_full[kb]), kTileBytes);
+            tma_load_2d(sA + kb * kTileBytes, &tmap, smem_u32(&sh->a_full[kb]), kb * kKB, a_row);
           }
         };
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
           // A is requested AFTER the item's first B tile: that tile only needs free ring slots, so it is in
-          // flight while the previous item's last MMAs (which still read the A blocks) retire
+          // flight while the previous item's last MMAs (which still read the A block) retire
           if (ct == 1) load_a();
           const int b_row = it.b_op * cap + ct * kBN;
-          // the tile's 128 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits
-          // on it directly).  The slot is rewritten by tile gt+4, whose first k-block reuses a ring slot last
-          // read by the MMAs of tile gt+2, which waited for the epilogue to drain tile gt (norms already in
-          // registers): no overwrite race.
+          // the tile's 256 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits
+          // on it directly).  The slot is rewritten by tile gt+4, whose first k-block reuses the ring slot last
+          // read by the MMAs of tile gt+3, which waited for the epilogue to drain tile gt+1 -- and a warp drains
+          // tile gt+1 only after it has finished the arithmetic (and norm reads) of tile gt: no overwrite race.
           const uint32_t nb_bar = smem_u32(&sh->nrm_full[gt % kNormRing]);
           for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
             const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
             mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
-            mbar_expect_tx(smem_u32(&sh->b_full[s]), kTileBytes);
-            tma_load_2d(sB + s * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB, b_row);
+            mbar_expect_tx(smem_u32(&sh->b_full[s]), kBSlotBytes);
+            for (int hb = 0; hb < kBN / kBM; ++hb)  // the tensor map's box is 128 rows: two boxes per k-block
+              tma_load_2d(sB + s * kBSlotBytes + hb * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB,
+                          b_row + hb * kBM);
             if (kb == 0) {
               mbar_expect_tx(nb_bar, kBN * 4);
               bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, nb_bar);
@@ -371,38 +365,35 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
           const int sa = gt % kAccStages, pha = (gt / kAccStages) & 1;
           mbar_wait(smem_u32(&sh->acc_empty[sa]), pha ^ 1);  // epilogue drained this accumulator stage
+          const uint32_t d = tmem_base + sa * kBN;
 #pragma unroll
           for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
             const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
-            if (ct == 0) mbar_wait(smem_u32(&sh->a_full[kb]), ai & 1);  // this k-slice of both A blocks landed
+            if (ct == 0) mbar_wait(smem_u32(&sh->a_full[kb]), ai & 1);  // this k-slice of the A block landed
             mbar_wait(smem_u32(&sh->b_full[s]), ph);                    // TMA landed this B k-block
             tc_fence_after();
 #pragma unroll
-            for (int b = 0; b < kABlocks; ++b) {
-              const uint32_t d = tmem_base + (sa * kABlocks + b) * kBN;
-#pragma unroll
-              for (int k = 0; k < kKB / 16; ++k) {
-                const uint64_t ad = umma_desc_sw128(sA + (b * kNumKB + kb) * kTileBytes + k * 32);
-                const uint64_t bd = umma_desc_sw128(sB + s * kTileBytes + k * 32);
-                tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
-              }
+            for (int k = 0; k < kKB / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sA + kb * kTileBytes + k * 32);
+              const uint64_t bd = umma_desc_sw128(sB + s * kBSlotBytes + k * 32);
+              tc_mma_bf16(d, ad, bd, idesc, (kb | k) != 0);
             }
-            tc_commit(smem_u32(&sh->b_empty[s]));  // ring slot free once these 8 MMAs retire
+            tc_commit(smem_u32(&sh->b_empty[s]));  // ring slot free once these 4 MMAs retire
           }
-          tc_commit(smem_u32(&sh->acc_full[sa]));  // both accumulators ready for the epilogue
+          tc_commit(smem_u32(&sh->acc_full[sa]));  // accumulator ready for the epilogue
         }
         ++ai;
-        tc_commit(smem_u32(&sh->a_empty));  // A blocks free once the item's last MMAs retire
+        tc_commit(smem_u32(&sh->a_empty));  // A block free once the item's last MMAs retire
       }
     }
   } else {
-    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; A row block = (warp - 2) / 4 =====
-    const int quad = warp & 3, blk = (warp - 2) >> 2;
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; 128-column half of the tile = (warp - 2) / 4 =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     uint32_t gt = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const TcItem it = tc_item(probs, P, w, nrb);
       if (!it.valid) continue;
-      const int row = it.rb * kItemRows + blk * kBM + quad * 32 + lane;
+      const int row = it.rb * kBM + quad * 32 + lane;
       uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
       const float off = key_offset(__uint_as_float(opmax[it.a_op]), __uint_as_float(opmax[it.b_op]));
       const uint32_t nmask = ~idx_mask;
@@ -413,20 +404,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         // the tile's column norms were bulk-copied to shared memory next to its B operand (broadcast LDS.128)
         mbar_wait(smem_u32(&sh->nrm_full[gt % kNormRing]), (gt / kNormRing) & 1);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int j0 = ct * kBN + half * 64;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cbase = half * 128 + hh * 64;  // first column of this 64-column group within the tile
+          const int j0 = ct * kBN + cbase;
           uint32_t acc[64];
-          tmem_ld64(tmem_base + (sa * kABlocks + blk) * kBN + half * 64 + ((uint32_t)(quad * 32) << 16), acc);
+          tmem_ld64(tmem_base + sa * kBN + cbase + ((uint32_t)(quad * 32) << 16), acc);
           float4 n4[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][half * 64 + 4 * e]);
+          for (int e = 0; e < 16; ++e) n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][cbase + 4 * e]);
           tmem_ld_wait();
-          if (half == 1) {
+          if (hh == 1) {
             tc_fence_before();
             epi_release(smem_u32(&sh->acc_empty[sa]), lane);  // accumulator is in registers: release it to the MMA warp
           }
-          // tile-local shortlist first: the column-in-tile index is an immediate of the packing LOP3 (one ALU op
+          // tile-local shortlist first: the column-in-group index is an immediate of the packing LOP3 (one ALU op
           // per element instead of add + LOP3); the three survivors get the column base OR-ed in afterwards
           uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu, l2 = 0xFFFFFFFFu;
 #pragma unroll
@@ -447,7 +438,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         }
       }
       if (row < it.Na) {
-        uint32_t* o = top_key + ((size_t)it.dp * cap + row) * kTop;
+        uint32_t* o = top_key + (((size_t)it.dp * cap + row) * kLists + half) * kTop;
         o[0] = k0;
         o[1] = k1;
         o[2] = k2;
@@ -486,10 +477,10 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
   if (Nb == 0) {
     resolved = true;
   } else if (Nb > kTop && !(mode == SPVO_MATCH_KNN_RATIO && !rev)) {
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kTop;
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int e = 0; e < kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const float off = key_offset(amax, bmax);
@@ -574,10 +565,10 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   (void)Na;
   if (Nb > 0) {
     // merge the two per-half shortlists: the kTop smallest packed keys of the row
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kTop;
+    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
     uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int e = 0; e < kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const float off = key_offset(amax, bmax);
@@ -950,7 +941,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
     if ((e = cudaMalloc((void**)&w->rr_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_count, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
     w->top_rows = top_rows;
   }
   return cudaSuccess;
@@ -978,7 +969,7 @@ static cudaError_t tc_get(Handle* h, TcWorkspace** w, size_t ops, size_t cap, si
 
 cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink) {
   TcWorkspace* w;
-  const int cap = (max_rows + kItemRows - 1) / kItemRows * kItemRows;
+  const int cap = (max_rows + kCapAlign - 1) / kCapAlign * kCapAlign;
   cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir);
   if (e != cudaSuccess) return e;
   w->slot_cap = cap;
@@ -1021,7 +1012,7 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
   if ((e = ensure_select_buffers(h, P, mr, mc)) != cudaSuccess) return e;
   if (max_rows > 0 && max_cols > 0) {
     const int mx = max_rows > max_cols ? max_rows : max_cols;
-    int cap = (mx + kItemRows - 1) / kItemRows * kItemRows;
+    int cap = (mx + kCapAlign - 1) / kCapAlign * kCapAlign;
     const bool cross = cfg.mode == SPVO_MATCH_NN_CROSSCHECK;
     const int ndir = cross ? 2 * P : P;
     TcWorkspace* w;
@@ -1046,11 +1037,11 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     const uint32_t idx_mask = (1u << idx_bits) - 1u;
     const float key_rel = 1.0f / (float)(1u << (23 - idx_bits));
     const float eps_rel = w->fp16 ? kEpsRelFp16 : kEpsRelBf16;
-    const size_t smem = 1024 + (size_t)(kABlocks * kNumKB + kBSlots) * kTileBytes + sizeof(TcShared);
+    const size_t smem = 1024 + (size_t)kNumKB * kTileBytes + (size_t)kBSlots * kBSlotBytes + sizeof(TcShared);
     if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
       LaunchScope ls(h, KID_TC_GEMM);
-      const int n_items = (cap / kItemRows) * ndir;
+      const int n_items = (cap / kBM) * ndir;
       const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
       k_tc_gemm<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
                                                 make_idesc(w->fp16), idx_mask, n_items);
