@@ -380,6 +380,27 @@ static int ensure_carry(Handle* h) {
 }
 
 // The device pipeline shared by both forms.  desc_out must be a device buffer [2F,K,256].
+struct CopyList {
+  CopySeg seg[8];
+  int n;
+};
+// Several small device-to-device copies in one launch (7 cudaMemcpyAsync nodes cost ~15 us of launch gaps per batch).
+__global__ void __launch_bounds__(256) k_carry_copy(const CopyList L) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < L.n; ++s) {
+    const CopySeg g = L.seg[s];
+    if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
+      const uint4* src = static_cast<const uint4*>(g.src);
+      uint4* dst = static_cast<uint4*>(g.dst);
+      for (size_t i = tid; i < g.bytes / 16; i += nth) dst[i] = src[i];
+    } else {
+      const uint32_t* src = static_cast<const uint32_t*>(g.src);
+      uint32_t* dst = static_cast<uint32_t*>(g.dst);
+      for (size_t i = tid; i < g.bytes / 4; i += nth) dst[i] = src[i];
+    }
+  }
+}
+
 static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int F, int H, int W,
                            const spvo_stereo_cfg* cfg, spvo_keypoint* kpts, float* desc_out, int* n_kpts,
                            spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep, spvo_quad* quads,
@@ -412,14 +433,21 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
     CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
                             cfg->min_disparity, keep));
   if (quads) CK(launch_consistency(h, F, K, matches, n_matches, q2t, keep, h->carry_map, quads, n_quads));
-  if (q2t)  // previous frame's L<->R map for the next batch's first frame (BASE:475-481)
-    CK(cudaMemcpyAsync(h->carry_map, q2t + (size_t)(F - 1) * K, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
-  // carry the last left image for the next batch's first temporal match
+  // Carry for the next batch in ONE launch: the previous frame's L<->R map (BASE:475-481) and the last left image
+  // (descriptors, keypoints, count, matcher operand slot) for the next batch's first temporal match.
+  CopyList cl;
+  cl.n = 0;
   const size_t last = (size_t)2 * (F - 1);
-  CK(cudaMemcpyAsync(h->carry_desc, desc_out + last * K * 256, (size_t)K * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(h->carry_kpts, kpts + last * K, (size_t)K * sizeof(spvo_keypoint), cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(h->carry_n, n_kpts + last, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  if (tensor) CK(tc_copy_slot(h, carry_slot, (int)last));
+  if (q2t) cl.seg[cl.n++] = {q2t + (size_t)(F - 1) * K, h->carry_map, (size_t)K * sizeof(int)};
+  cl.seg[cl.n++] = {desc_out + last * K * 256, h->carry_desc, (size_t)K * 256 * sizeof(float)};
+  cl.seg[cl.n++] = {kpts + last * K, h->carry_kpts, (size_t)K * sizeof(spvo_keypoint)};
+  cl.seg[cl.n++] = {n_kpts + last, h->carry_n, sizeof(int)};
+  if (tensor) cl.n += tc_copy_slot_segments(h, carry_slot, (int)last, cl.seg + cl.n);
+  {
+    LaunchScope ls(h, KID_CARRY);
+    k_carry_copy<<<96, 256, 0, st>>>(cl);
+  }
+  CK(cudaGetLastError());
   h->carry_tc_valid = tensor;
   h->has_prev = true;
   return SPVO_OK;
@@ -522,7 +550,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency", "k_carry_copy"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

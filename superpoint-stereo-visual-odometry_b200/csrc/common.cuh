@@ -24,7 +24,7 @@ struct Handle;
 // (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
 enum KernelId {
   KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
-  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_CONSISTENCY, KID_COUNT
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_CONSISTENCY, KID_CARRY, KID_COUNT
 };
 struct ProfRec {
   int kid;
@@ -62,7 +62,14 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
                             bool operands_ready = false);
 // Stereo pipeline: reserve max_batch image slots + 1 carry slot and return where decode should write.
 cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink);
-cudaError_t tc_copy_slot(Handle* h, int dst_slot, int src_slot);
+// One device-to-device copy segment of k_carry_copy (sizes are multiples of 4 bytes).
+struct CopySeg {
+  const void* src;
+  void* dst;
+  unsigned long long bytes;
+};
+// The three segments (16-bit rows, squared norms, max norm) that copy operand slot src_slot to dst_slot; returns 3.
+int tc_copy_slot_segments(Handle* h, int dst_slot, int src_slot, CopySeg* segs);
 cudaError_t tc_prep_problem_operands(Handle* h, const MatchProblem* prob);  // k_tc_prep for one problem's q and t
 void tc_workspace_free(Handle* h);
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,

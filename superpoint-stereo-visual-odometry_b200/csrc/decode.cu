@@ -99,6 +99,7 @@ struct DetectParams {
   int* n_out;
   unsigned long long* counters;
   int4* kp_par;   // [B,K] sampling parameters for k_desc_planes (may be NULL)
+  unsigned* opmax_zero;  // [B] matcher operand max-norm slots to clear for k_desc_normalize (may be NULL)
   size_t bitmap_stride;  // words per image in `bitmap`
   unsigned* bitmap;  // [B, bitmap_stride] global scratch: pixels suppressed by earlier chunks (multi-chunk path only)
   int cap;        // key buffer capacity (power of two)
@@ -426,6 +427,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   if (tid == 0) {
     s_emitted = 0;
     s_bin = kHistBins - 1;
+    if (p.opmax_zero) p.opmax_zero[b] = 0u;  // k_desc_normalize takes an atomicMax into it (saves a memset node)
   }
 
   // ---- first-chunk threshold from the sampled histogram (estimate only) ------------------------
@@ -896,6 +898,7 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
     const int Kp = (K + 3) & ~3;  // scratch pitch: 16-byte loads in k_desc_normalize
     float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * Kp : nullptr;
     p.kp_par = kp_par;
+    p.opmax_zero = (streaming && sink && sink->opmax) ? sink->opmax + b0 : nullptr;
     p.bitmap = h->nms_bitmap + (size_t)b0 * ((size_t)h->max_h * h->max_w / 16 + 64);
     p.bitmap_stride = (size_t)h->max_h * h->max_w / 16 + 64;
     p.cap = K <= 1536 ? 4096 : 8192;
@@ -916,7 +919,6 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
         sk.xb = reinterpret_cast<unsigned short*>(sk.xb) + (size_t)b0 * sk.cap * 256;
         sk.nrm += (size_t)b0 * sk.cap;
         sk.opmax += b0;
-        if ((e = cudaMemsetAsync(sk.opmax, 0, (size_t)B * sizeof(unsigned), st)) != cudaSuccess) return e;
       }
       const int rows = sk.xb ? sk.cap : K;
       // Optional grouping of images (tuning knob).  Measured on B200 at 148 images: one launch over the whole

@@ -895,7 +895,6 @@ struct TcWorkspace {
   float* nrm = nullptr;
   unsigned* opmax = nullptr;
   uint32_t* top_key = nullptr;
-  int* fb_count = nullptr;
   int* fb_list = nullptr;
   int* rr_count = nullptr;  // rows queued by k_tc_triage for k_tc_rerank
   int* rr_list = nullptr;
@@ -931,15 +930,13 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
   const size_t top_rows = ndir * cap;
   if (w->top_rows < top_rows) {
     if (w->top_key) cudaFree(w->top_key);
-    if (w->fb_count) cudaFree(w->fb_count);
     if (w->fb_list) cudaFree(w->fb_list);
     if (w->rr_count) cudaFree(w->rr_count);
     if (w->rr_list) cudaFree(w->rr_list);
-    w->top_key = nullptr; w->fb_count = nullptr; w->fb_list = nullptr; w->rr_count = nullptr; w->rr_list = nullptr;
+    w->top_key = nullptr; w->fb_list = nullptr; w->rr_count = nullptr; w->rr_list = nullptr;
     w->top_rows = 0;
-    if ((e = cudaMalloc((void**)&w->rr_count, top_rows * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->rr_count, 2 * top_rows * sizeof(int))) != cudaSuccess) return e;  // + the fallback counters
     if ((e = cudaMalloc((void**)&w->rr_list, top_rows * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&w->fb_count, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
     w->top_rows = top_rows;
@@ -950,7 +947,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
 void tc_workspace_free(Handle* h) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
   if (!w) return;
-  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_count, w->fb_list, w->rr_count, w->rr_list};
+  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_list, w->rr_count, w->rr_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete w;
@@ -982,16 +979,14 @@ cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSin
   return cudaSuccess;
 }
 
-cudaError_t tc_copy_slot(Handle* h, int dst, int src) {
+int tc_copy_slot_segments(Handle* h, int dst, int src, CopySeg* segs) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
-  if (!w) return cudaErrorInvalidValue;
+  if (!w) return 0;
   const size_t cap = w->slot_cap;
-  cudaError_t e;
-  if ((e = cudaMemcpyAsync(w->xb + (size_t)dst * cap * kDim, w->xb + (size_t)src * cap * kDim,
-                           cap * kDim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, h->stream)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyAsync(w->nrm + (size_t)dst * cap, w->nrm + (size_t)src * cap, cap * sizeof(float),
-                           cudaMemcpyDeviceToDevice, h->stream)) != cudaSuccess) return e;
-  return cudaMemcpyAsync(w->opmax + dst, w->opmax + src, sizeof(unsigned), cudaMemcpyDeviceToDevice, h->stream);
+  segs[0] = {w->xb + (size_t)src * cap * kDim, w->xb + (size_t)dst * cap * kDim, cap * kDim * sizeof(__nv_bfloat16)};
+  segs[1] = {w->nrm + (size_t)src * cap, w->nrm + (size_t)dst * cap, cap * sizeof(float)};
+  segs[2] = {w->opmax + src, w->opmax + dst, sizeof(unsigned)};
+  return 3;
 }
 
 cudaError_t tc_prep_problem_operands(Handle* h, const MatchProblem* prob) {
@@ -1029,8 +1024,9 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       LaunchScope ls(h, KID_TC_PREP);
       k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap, 0);
     }
-    if ((e = cudaMemsetAsync(w->fb_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(w->rr_count, 0, (size_t)ndir * sizeof(int), st)) != cudaSuccess) return e;
+    // one memset for both worklist counters: fb_count sits right behind the ndir rerank counters of this call
+    int* const fb_count = w->rr_count + ndir;
+    if ((e = cudaMemsetAsync(w->rr_count, 0, (size_t)2 * ndir * sizeof(int), st)) != cudaSuccess) return e;
     int idx_bits = 7;
     while ((1 << idx_bits) < cap) ++idx_bits;
     if (idx_bits > kMaxIdxBits) return cudaErrorInvalidValue;
@@ -1055,13 +1051,13 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     {
       LaunchScope ls(h, KID_TC_RERANK);
       k_tc_rerank<<<dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
-                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, w->fb_count,
+                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, fb_count,
                                                      w->fb_list, h->counters, eps_rel, idx_mask, key_rel, w->rr_count,
                                                      w->rr_list);
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
-      k_tc_fallback<<<ndir, 256, 0, st>>>(probs, P, cfg.mode, w->nrm, cap, mr, mc, w->fb_count, w->fb_list,
+      k_tc_fallback<<<ndir, 256, 0, st>>>(probs, P, cfg.mode, w->nrm, cap, mr, mc, fb_count, w->fb_list,
                                           h->row_best, h->row_d, h->col_best, h->counters);
     }
     if (cfg.mode != SPVO_MATCH_KNN_RATIO) {
