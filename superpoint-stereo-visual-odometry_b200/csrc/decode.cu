@@ -199,22 +199,28 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const float* _
   }
   __syncthreads();
   const uint32_t lo_b = (uint32_t)(lo >> 32);
-  for (int c0 = 0; c0 < cells; c0 += kDetectThreads) {
-    const int c = c0 + threadIdx.x;
-    bool q = false;
-    if (c < cells) {
-      const uint32_t mb = fbits(__ldg(cellmax + c));
-      q = mb > conf_bits && mb >= lo_b;
+  constexpr int kPU = 4;  // cell maxima in flight per thread (the loop is latency-bound: one CTA per image)
+  for (int c0 = 0; c0 < cells; c0 += kPU * kDetectThreads) {
+    uint32_t mb[kPU];
+#pragma unroll
+    for (int u = 0; u < kPU; ++u) {
+      const int c = c0 + u * kDetectThreads + threadIdx.x;
+      mb[u] = c < cells ? fbits(__ldg(cellmax + c)) : 0u;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, q);
-    if (m) {
-      int basei = 0;
-      const int leader = __ffs(m) - 1;
-      if (lane == leader) basei = atomicAdd(s_ncell, __popc(m));
-      basei = __shfl_sync(0xffffffffu, basei, leader);
-      if (q) {
-        const int slot = basei + __popc(m & ((1u << lane) - 1u));
-        if (slot < list_cap) cell_list[slot] = (uint16_t)c;
+#pragma unroll
+    for (int u = 0; u < kPU; ++u) {
+      const int c = c0 + u * kDetectThreads + threadIdx.x;
+      const bool q = c < cells && mb[u] > conf_bits && mb[u] >= lo_b;
+      const unsigned m = __ballot_sync(0xffffffffu, q);
+      if (m) {
+        int basei = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) basei = atomicAdd(s_ncell, __popc(m));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (q) {
+          const int slot = basei + __popc(m & ((1u << lane) - 1u));
+          if (slot < list_cap) cell_list[slot] = (uint16_t)c;
+        }
       }
     }
   }
@@ -223,7 +229,7 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const float* _
   if (ncell > list_cap) return -1;
   // half a warp per cell: lane l16 reads row l16/2, float4 l16&1 of the cell's 8x8 block
   const int l16 = lane & 15, half = lane >> 4, row = l16 >> 1, part = l16 & 1;
-  constexpr int kCU = 4;
+  constexpr int kCU = 4;  // cells (16-byte loads) in flight per thread
   const int per_iter = (kDetectThreads / 32) * 2 * kCU;
   for (int base = 0; base < ncell; base += per_iter) {
     float4 v[kCU];
@@ -243,23 +249,41 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const float* _
         v[u] = __ldg(reinterpret_cast<const float4*>(heat + (size_t)cy[u] * W + cx[u]));
       }
     }
+    // Hits are rare (about one pixel per fetched cell), so each thread first marks its hits in a 32-bit mask
+    // (2-3 instructions per pixel), the warp reserves its key slots with ONE scan + ONE shared atomic, and only
+    // then are the keys built and stored (predicated, in pixel order).
+    uint32_t mask = 0u;
 #pragma unroll
     for (int u = 0; u < kCU; ++u) {
       const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const uint32_t bts = fbits(pv[e]);
-        const u64 key = make_key(bts, cx[u] + e, cy[u], H);
-        const bool s = ok[u] && bts > conf_bits && key >= lo;
-        const unsigned m = __ballot_sync(0xffffffffu, s);
-        if (m) {
-          int basei = 0;
-          const int leader = __ffs(m) - 1;
-          if (lane == leader) basei = atomicAdd(s_count, __popc(m));
-          basei = __shfl_sync(0xffffffffu, basei, leader);
-          if (s) {
-            const int slot = basei + __popc(m & ((1u << lane) - 1u));
-            if (slot < cap) keys[slot] = key;
+        bool s = ok[u] && bts > conf_bits && bts >= lo_b;
+        if (s && bts == lo_b) s = make_key(bts, cx[u] + e, cy[u], H) >= lo;  // boundary score: full key comparison
+        mask |= (s ? 1u : 0u) << (4 * u + e);
+      }
+    }
+    const int cnt = __popc(mask);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int basei = 0;
+    if (lane == 31 && inc > 0) basei = atomicAdd(s_count, inc);
+    basei = __shfl_sync(0xffffffffu, basei, 31);
+    int slot = basei + inc - cnt;
+    if (mask) {
+#pragma unroll
+      for (int u = 0; u < kCU; ++u) {
+        const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (mask & (1u << (4 * u + e))) {
+            if (slot < cap) keys[slot] = make_key(fbits(pv[e]), cx[u] + e, cy[u], H);
+            ++slot;
           }
         }
       }
