@@ -100,7 +100,7 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   h->stream = h->own_stream;
   ALLOC(h->heat, (size_t)max_batch * px * sizeof(float));
   ALLOC(h->hist, (size_t)max_batch * kHistBins * sizeof(unsigned));
-  ALLOC(h->cellmax, (size_t)max_batch * cells * sizeof(float));
+  ALLOC(h->cellmax, (size_t)max_batch * cells * sizeof(uint2));
   ALLOC(h->nms_bitmap, (size_t)max_batch * (px / 16 + 64) * sizeof(unsigned));  // H*ceil(W/32) <= H*W/16 for W >= 16
   ALLOC(h->counters, 8 * sizeof(unsigned long long));
   cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long));

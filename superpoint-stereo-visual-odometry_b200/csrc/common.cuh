@@ -94,7 +94,7 @@ struct Handle {
   // decode workspace
   float* heat = nullptr;          // [max_batch, max_h*max_w]
   unsigned* hist = nullptr;       // [max_batch, kHistBins]
-  float* cellmax = nullptr;       // [max_batch, cells] per-cell heatmap maximum
+  uint2* cellmax = nullptr;       // [max_batch, cells] per-cell (max, second max | argmax) records of the heatmap
   unsigned* nms_bitmap = nullptr; // [max_batch, max_h*ceil(max_w/32)] suppression bitmap of the multi-chunk path
   float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)
   int4* kp_par = nullptr;         // [max_batch, max_k] sampling parameters

@@ -33,7 +33,7 @@ namespace spvo {
 constexpr int kHeatThreads = 128;
 __global__ void __launch_bounds__(kHeatThreads, 4)
 k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
-               float* __restrict__ cellmax, int Hc, int Wc, float conf) {
+               uint2* __restrict__ cellmax, int Hc, int Wc, float conf) {
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
@@ -54,14 +54,17 @@ k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigne
   const int hc = cell / Wc, wc = cell - hc * Wc;
   const int W = Wc * 8;
   float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc) * W + 8 * wc;
-  float cm = 0.0f;
+  float m1 = 0.0f, m2 = 0.0f;  // largest and second largest pixel of the cell (m2 == m1 on ties)
+  int arg = 0;                 // pixel index 8 * row + col of the largest
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     float p[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       p[j] = __fdiv_rn(e[8 * r + j], denom);
-      cm = fmaxf(cm, p[j]);
+      m2 = fmaxf(m2, fminf(m1, p[j]));
+      arg = p[j] > m1 ? 8 * r + j : arg;
+      m1 = fmaxf(m1, p[j]);
     }
     reinterpret_cast<float4*>(dst + (size_t)r * W)[0] = make_float4(p[0], p[1], p[2], p[3]);
     reinterpret_cast<float4*>(dst + (size_t)r * W)[1] = make_float4(p[4], p[5], p[6], p[7]);
@@ -77,8 +80,10 @@ k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigne
       atomicAdd(&hist[(size_t)b * kHistBins + bin], 1u);
     }
   }
-  // per-cell maximum: lets k_detect skip cells that cannot hold a first-chunk candidate
-  cellmax[(size_t)b * cells + cell] = cm;
+  // Per-cell record for k_detect: .x = bits of the cell maximum, .y = bits of the second largest pixel with the
+  // low 6 bits replaced by the argmax.  Cells that cannot hold a first-chunk candidate are skipped; cells whose
+  // second pixel is below the chunk's bound yield their single candidate without touching the heatmap.
+  cellmax[(size_t)b * cells + cell] = make_uint2(fbits(m1), (fbits(m2) & ~63u) | (uint32_t)arg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,7 +94,7 @@ k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigne
 // ------------------------------------------------------------------------------------------------
 struct DetectParams {
   const float* heat;
-  const float* cellmax;  // [B, cells] per-cell maximum of the heatmap
+  const uint2* cellmax;  // [B, cells] per-cell (max bits, second-max bits | argmax) records of the heatmap
   const unsigned* hist;
   int H, W;
   float conf;
@@ -188,7 +193,7 @@ __device__ int collect_keys(const float* heat, int H, int W, uint32_t conf_bits,
 // lower bound are fetched (8 rows x 32 B each), instead of streaming the whole heatmap.  Returns the
 // number of keys >= lo (first `cap` stored), or -1 if more than `list_cap` cells qualify (caller then
 // falls back to the full scan).  hi is unbounded here.
-__device__ int collect_keys_cells(const float* __restrict__ heat, const float* __restrict__ cellmax, int H, int W,
+__device__ int collect_keys_cells(const float* __restrict__ heat, const uint2* __restrict__ cellmax, int H, int W,
                                   uint32_t conf_bits, u64 lo, u64* keys, int cap, uint16_t* cell_list, int list_cap,
                                   int* s_count, int* s_ncell) {
   const int Wc = W >> 3, cells = (H >> 3) * Wc;
@@ -199,27 +204,50 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const float* _
   }
   __syncthreads();
   const uint32_t lo_b = (uint32_t)(lo >> 32);
-  constexpr int kPU = 4;  // cell maxima in flight per thread (the loop is latency-bound: one CTA per image)
+  constexpr int kPU = 4;  // cell records in flight per thread (the loop is latency-bound: one CTA per image)
   for (int c0 = 0; c0 < cells; c0 += kPU * kDetectThreads) {
-    uint32_t mb[kPU];
+    uint2 rec[kPU];
 #pragma unroll
     for (int u = 0; u < kPU; ++u) {
       const int c = c0 + u * kDetectThreads + threadIdx.x;
-      mb[u] = c < cells ? fbits(__ldg(cellmax + c)) : 0u;
+      rec[u] = c < cells ? __ldg(cellmax + c) : make_uint2(0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < kPU; ++u) {
       const int c = c0 + u * kDetectThreads + threadIdx.x;
-      const bool q = c < cells && mb[u] > conf_bits && mb[u] >= lo_b;
-      const unsigned m = __ballot_sync(0xffffffffu, q);
-      if (m) {
+      const uint32_t mb = rec[u].x;
+      const bool q = c < cells && mb > conf_bits && mb >= lo_b;
+      // (second | 63) bounds the second largest pixel from above: below the chunk's bound (or the confidence
+      // threshold) means the maximum is the cell's ONLY candidate, and its position is in the record
+      const uint32_t sb = rec[u].y | 63u;
+      const bool multi = q && sb > conf_bits && sb >= lo_b;
+      bool single = q && !multi;
+      u64 key = 0ull;
+      if (single) {
+        const int hc = c / Wc, wc = c - hc * Wc, a = (int)(rec[u].y & 63u);
+        key = make_key(mb, 8 * wc + (a & 7), 8 * hc + (a >> 3), H);
+        single = key >= lo;
+      }
+      const unsigned mm = __ballot_sync(0xffffffffu, multi);
+      if (mm) {
         int basei = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) basei = atomicAdd(s_ncell, __popc(m));
+        const int leader = __ffs(mm) - 1;
+        if (lane == leader) basei = atomicAdd(s_ncell, __popc(mm));
         basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (q) {
-          const int slot = basei + __popc(m & ((1u << lane) - 1u));
+        if (multi) {
+          const int slot = basei + __popc(mm & ((1u << lane) - 1u));
           if (slot < list_cap) cell_list[slot] = (uint16_t)c;
+        }
+      }
+      const unsigned ms = __ballot_sync(0xffffffffu, single);
+      if (ms) {
+        int basei = 0;
+        const int leader = __ffs(ms) - 1;
+        if (lane == leader) basei = atomicAdd(s_count, __popc(ms));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (single) {
+          const int slot = basei + __popc(ms & ((1u << lane) - 1u));
+          if (slot < cap) keys[slot] = key;
         }
       }
     }
@@ -903,7 +931,7 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
   if (scores) scores += (size_t)b0 * K;
   float* heat = h->heat + (size_t)b0 * H * W;
   unsigned* hist = h->hist + (size_t)b0 * kHistBins;
-  float* cellmax = h->cellmax + (size_t)b0 * cells;
+  uint2* cellmax = h->cellmax + (size_t)b0 * cells;
   if ((e = cudaMemsetAsync(hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
   dim3 g1((cells + kHeatThreads - 1) / kHeatThreads, B);
   {
