@@ -386,18 +386,26 @@ struct CopyList {
 };
 // Several small device-to-device copies in one launch (7 cudaMemcpyAsync nodes cost ~15 us of launch gaps per batch).
 __global__ void __launch_bounds__(256) k_carry_copy(const CopyList L) {
+  // blockIdx.y = segment: all segments (and all of a segment's 16-byte loads) are in flight together
+  const CopySeg g = L.seg[blockIdx.y];
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  for (int s = 0; s < L.n; ++s) {
-    const CopySeg g = L.seg[s];
-    if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
-      const uint4* src = static_cast<const uint4*>(g.src);
-      uint4* dst = static_cast<uint4*>(g.dst);
-      for (size_t i = tid; i < g.bytes / 16; i += nth) dst[i] = src[i];
-    } else {
-      const uint32_t* src = static_cast<const uint32_t*>(g.src);
-      uint32_t* dst = static_cast<uint32_t*>(g.dst);
-      for (size_t i = tid; i < g.bytes / 4; i += nth) dst[i] = src[i];
+  if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
+    const uint4* src = static_cast<const uint4*>(g.src);
+    uint4* dst = static_cast<uint4*>(g.dst);
+    const size_t n = g.bytes / 16;
+    for (size_t i = tid; i < n; i += 4 * nth) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * nth < n) v[u] = src[i + u * nth];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * nth < n) dst[i + u * nth] = v[u];
     }
+  } else {
+    const uint32_t* src = static_cast<const uint32_t*>(g.src);
+    uint32_t* dst = static_cast<uint32_t*>(g.dst);
+    for (size_t i = tid; i < g.bytes / 4; i += nth) dst[i] = src[i];
   }
 }
 
@@ -445,7 +453,7 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   if (tensor) cl.n += tc_copy_slot_segments(h, carry_slot, (int)last, cl.seg + cl.n);
   {
     LaunchScope ls(h, KID_CARRY);
-    k_carry_copy<<<96, 256, 0, st>>>(cl);
+    k_carry_copy<<<dim3(64, cl.n), 256, 0, st>>>(cl);
   }
   CK(cudaGetLastError());
   h->carry_tc_valid = tensor;
