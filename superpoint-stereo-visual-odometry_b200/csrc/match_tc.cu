@@ -9,10 +9,10 @@
 //                   Not used by the stereo pipeline: k_desc_normalize (decode.cu) writes fp16 operands of
 //                   its unit-norm descriptors straight into the workspace.
 //   k_tc_gemm       persistent, one CTA per SM over (directed problem, 128-row block) items:
-//                   S = A . B^T with tcgen05.mma (cta_group::1, M = N = 128, K = 16, 16-bit -> fp32 in
-//                   TMEM), B tiles staged by TMA (128 B swizzle) through a 2-stage mbarrier pipeline,
-//                   accumulators double buffered in TMEM; 8 epilogue warps read TMEM with tcgen05.ld and
-//                   keep, per row, the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN
+//                   S = A . B^T with tcgen05.mma (cta_group::1, M = 128, N = 256, K = 16, 16-bit -> fp32 in
+//                   TMEM), A block resident per item, B streamed by TMA (128 B swizzle) as a ring of 32 KB
+//                   k-blocks, two 256-column accumulators in TMEM; 8 epilogue warps read TMEM with tcgen05.ld
+//                   and keep, per row, the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN
 //                   REGISTERS as packed keys (the distance matrix never exists in memory)
 //   k_tc_triage     one thread per row: rows whose 2nd shortlist entry is outside the proved error bound
 //                   are decided with no further arithmetic; the rest are queued
