@@ -37,6 +37,8 @@ def _compare(fe, O, semi, desc, **cfg):
     (360, 1176, 1000, 0.1),   # repo-native size, heavy score ties
     (240, 784, 1000, 3.0),
     (120, 392, 1000, 1.0),    # reference default ctor size: fewer survivors than K
+    (128, 320, 333, 1.0),     # K not a multiple of 4: scratch pitch / 16-byte loads of k_desc_normalize
+    (64, 64, 7, 1.0),         # tiny: a single 128-cell block of k_softmax_heat, 32-key sort
 ])
 def test_decode_parity(spvo, oracle, H, W, K, sigma):
     fe = spvo.Frontend(0, 2, H, W, K)

@@ -121,3 +121,24 @@ def test_stereo_batch_host_chunked_path(spvo, oracle):
         _check_batch(S, out, ref, b * F, F, K)
     assert sum(len(r["quads"]) for r in ref) > 50
     fe.close()
+
+
+@pytest.mark.parametrize("K", [333, 130])
+def test_stereo_batch_odd_keypoint_budget(spvo, oracle, K):
+    """K that is not a multiple of 4 / 16 / 256: the scratch pitch, the padded matcher slots (cap = K rounded to
+    256) and the unaligned segments of the one-launch carry copy, on both matcher algorithms."""
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, F, NB = 128, 320, 2, 2
+    semi, desc = synth.make_stream(F * NB, H, W, seed=21, device="cpu")
+    semi, desc = semi.numpy(), desc.numpy()
+    ref = _oracle_stream(oracle, semi, desc, K, 1, 2.0, 0.25)
+    assert all(int(r["dec"]["n"][0]) == K for r in ref), "the budget must bind so that n == K (odd row counts)"
+    for alg in (S.MATCHER_TENSOR, S.MATCHER_EXACT_FP32):
+        fe = S.Frontend(0, 2 * F, H, W, K)
+        for b in range(NB):
+            out = {k: v.numpy() for k, v in fe.alloc_stereo_out(F, K, device="cpu").items()}
+            fe.stereo_batch(semi[b * F:(b + 1) * F], desc[b * F:(b + 1) * F], F, H, W, out, max_keypoints=K, mode=1,
+                            algorithm=alg)
+            _check_batch(S, out, ref, b * F, F, K)
+        fe.close()
