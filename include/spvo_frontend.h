@@ -107,6 +107,21 @@ int spvo_abi_version(void);
 int spvo_set_stream(spvo_handle h, void* cuda_stream);
 int spvo_sync(spvo_handle h);
 
+/* ---- preprocess (the step before the network): replaces FeatureFrontEnd::preprocessImageImpl (BASE:68-121) and
+ * the 8U -> 32F hand-over of SuperPointFeatureFrontEnd::preprocessImage (NN:139-161): centre crop to the aspect
+ * ratio W:H, cv::resize(INTER_LINEAR) of the 8UC1 image to W x H (OpenCV's fixed-point arithmetic, bit for bit),
+ * input = pixel * (1/255).
+ *   imgs        [B, rows, stride] 8UC1, stride >= cols bytes per row (a batch of equally sized camera images)
+ *   input_out   [B, H, W] fp32   = input_data_ (HPP:382), the network's input block; may be NULL
+ *   resized_out [B, H, W] u8     = the image the reference keeps in images_dq (NN:153); may be NULL
+ *   proj        [B][12] optional, HOST memory in both forms: 3x4 row-major projection matrices, patched in place
+ *               (principal point minus the crop offset, rows 0-1 times W / cropped_cols: BASE:93, 109, 119-120)
+ * H and W need not be multiples of 8 here.  Host-pointer form copies in, runs, copies out, synchronises. */
+int spvo_preprocess(spvo_handle h, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                    float* input_out, uint8_t* resized_out, float* proj);
+int spvo_preprocess_device(spvo_handle h, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                           float* input_out, uint8_t* resized_out, float* proj);
+
 /* ---- decode: replaces SuperPointFeatureFrontEnd::postprocessDetectionAndDescription()
  * (HPP:327, NN:264-364) including processOneHeatmap (NN:188-262) and bilinearInterpolationDesc
  * (NN:366-431).

@@ -58,6 +58,10 @@ def lib():
         L.spvo_oracle_stereo_filter.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
         L.spvo_oracle_consistency.restype = C.c_int
         L.spvo_oracle_consistency.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.spvo_oracle_crop_geometry.restype = C.c_int
+        L.spvo_oracle_crop_geometry.argtypes = [C.c_int] * 4 + [ip] * 4
+        L.spvo_oracle_preprocess.restype = C.c_int
+        L.spvo_oracle_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -153,3 +157,23 @@ def consistency(stereo_matches, map_t, keep, map_prev) -> np.ndarray:
     out = np.zeros((max(len(m), 1), 4), np.int32)
     n = lib().spvo_oracle_consistency(_p(m), len(m), _p(mt), _p(kp), _p(mp), _p(out))
     return out[:n].copy()
+
+
+def crop_geometry(rows, cols, H, W):
+    """(crop_rows, crop_cols, row_offset, col_offset) of BASE:71-113."""
+    v = [C.c_int(0) for _ in range(4)]
+    if lib().spvo_oracle_crop_geometry(rows, cols, H, W, *[C.byref(x) for x in v]):
+        raise ValueError("spvo_oracle_crop_geometry: invalid arguments")
+    return tuple(x.value for x in v)
+
+
+def preprocess(img, H, W, P=None):
+    """img [rows, cols] uint8 -> (input [H,W] float32, resized [H,W] uint8, patched P [3,4] or None)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape
+    inp = np.empty((H, W), np.float32)
+    rs = np.empty((H, W), np.uint8)
+    Pm = None if P is None else np.ascontiguousarray(P, np.float32).reshape(3, 4).copy()
+    if lib().spvo_oracle_preprocess(_p(img), rows, cols, cols, H, W, _p(inp), _p(rs), _p(Pm)):
+        raise ValueError("spvo_oracle_preprocess: invalid arguments")
+    return inp, rs, Pm

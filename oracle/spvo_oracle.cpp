@@ -11,6 +11,8 @@
 //            src/feature_detection_neural_network.cpp:332-431  bilinear descriptor sampling + L2 norm
 //   match    src/feature_detection_base.cpp:10-33, 434-500      cv::BFMatcher NN(+cross-check) / kNN-2 + ratio
 //   filter   src/feature_detection_base.cpp:169-172             stereo row-band / min-disparity test
+//   preproc  src/feature_detection_base.cpp:68-121, src/feature_detection_neural_network.cpp:139-161
+//            centre crop to the network's aspect ratio, cv::resize(INTER_LINEAR) on 8UC1, /255, P-matrix patch
 //
 // Parity pin status.  The reference has NO tests, golden vectors or fixtures for this path
 // (SURVEY.md section 4), and its decode cannot be compiled here (needs Eigen, OpenCV C++ headers,
@@ -24,6 +26,8 @@
 //     arithmetic below (hal::normL2Sqr_ lane order + sqrt, first-index ties, mutual-argmin
 //     cross-check, stable top-2) is checked bit-for-bit against cv2 in tests/test_oracle_match.py
 //     and against committed cv2-generated fixtures in tests/golden/.
+//   * PREPROCESS: the resize is pinned bit-for-bit against cv2.resize (tests/test_oracle_preprocess.py, live and
+//     through committed cv2-generated fixtures); crop / P-matrix / scaling are plain fp32 statements of BASE:68-121.
 //
 // Build: see oracle/Makefile (g++ -O2 -mavx2 -mfma -ffp-contract=off; no fast-math, so every
 // fp32 operation below is a single correctly rounded IEEE operation in the order written).
@@ -442,6 +446,93 @@ int spvo_oracle_consistency(const spvo_dmatch* stereo, int n, const int* map_t, 
     ++k;
   }
   return k;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// preprocessImage (BASE:68-121 + NN:139-161): crop -> cv::resize(INTER_LINEAR, 8UC1) -> * (1/255)
+// ---------------------------------------------------------------------------------------------
+// Crop geometry of BASE:71-113 (int <- float conversions truncate, as the C++ assignments do).
+int spvo_oracle_crop_geometry(int rows, int cols, int H, int W, int* crop_rows, int* crop_cols, int* row_off,
+                              int* col_off) {
+  if (rows <= 0 || cols <= 0 || H <= 0 || W <= 0) return -1;
+  int img_rows = rows, img_cols = cols, ro = 0, co = 0;
+  const float real_ar = static_cast<float>(cols) / static_cast<float>(rows);
+  const float expected_ar = static_cast<float>(W) / static_cast<float>(H);
+  if (expected_ar > real_ar) {
+    img_rows = static_cast<int>(static_cast<float>(img_cols) / expected_ar);  // BASE:85
+    ro = (rows - img_rows) / 2;
+  } else if (expected_ar < real_ar) {
+    img_cols = static_cast<int>(static_cast<float>(img_rows) * expected_ar);  // BASE:101
+    co = (cols - img_cols) / 2;
+  }
+  if (img_rows <= 0 || img_cols <= 0) return -1;
+  *crop_rows = img_rows; *crop_cols = img_cols; *row_off = ro; *col_off = co;
+  return 0;
+}
+
+// cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_LINEAR) for 8UC1, OpenCV's fixed-point path
+// (imgproc/src/resize.cpp: 11-bit coefficients, HResizeLinear to int, VResizeLinear<uchar,...>);
+// an exact 2x decimation takes OpenCV's INTER_AREA fast path ((a+b+c+d+2)>>2).
+static void resize_linear_8u(const uint8_t* src, int sh, int sw, int sstride, uint8_t* dst, int dh, int dw) {
+  if (dw * 2 == sw && dh * 2 == sh) {
+    for (int y = 0; y < dh; ++y)
+      for (int x = 0; x < dw; ++x) {
+        const uint8_t* p = src + (size_t)(2 * y) * sstride + 2 * x;
+        dst[(size_t)y * dw + x] = (uint8_t)((p[0] + p[1] + p[sstride] + p[sstride + 1] + 2) >> 2);
+      }
+    return;
+  }
+  const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+  std::vector<int> xofs(dw), xofs1(dw), a0(dw), a1(dw);
+  for (int dx = 0; dx < dw; ++dx) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
+    xofs[dx] = sx;
+    xofs1[dx] = std::min(sx + 1, sw - 1);
+    a0[dx] = (int)std::lrintf((1.f - fx) * 2048.f);  // saturate_cast<short>: round half to even, no saturation here
+    a1[dx] = (int)std::lrintf(fx * 2048.f);
+  }
+  std::vector<int> row0(dw), row1(dw);
+  for (int dy = 0; dy < dh; ++dy) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)std::floor(fy);
+    fy -= sy;
+    const int b0 = (int)std::lrintf((1.f - fy) * 2048.f), b1 = (int)std::lrintf(fy * 2048.f);
+    const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
+    const uint8_t* s0 = src + (size_t)y0 * sstride;
+    const uint8_t* s1 = src + (size_t)y1 * sstride;
+    for (int dx = 0; dx < dw; ++dx) {
+      row0[dx] = s0[xofs[dx]] * a0[dx] + s0[xofs1[dx]] * a1[dx];
+      row1[dx] = s1[xofs[dx]] * a0[dx] + s1[xofs1[dx]] * a1[dx];
+    }
+    for (int dx = 0; dx < dw; ++dx)
+      dst[(size_t)dy * dw + dx] = (uint8_t)((((b0 * (row0[dx] >> 4)) >> 16) + ((b1 * (row1[dx] >> 4)) >> 16) + 2) >> 2);
+  }
+}
+
+// img [rows, stride] 8UC1 -> resized [H, W] u8 (the image the reference keeps in images_dq, may be NULL) and
+// input [H, W] fp32 = resized * (1/255) (NN:159).  P: 3x4 row-major projection matrix patched in place (may be NULL).
+int spvo_oracle_preprocess(const uint8_t* img, int rows, int cols, int stride, int H, int W, float* input,
+                           uint8_t* resized, float* P) {
+  int cr, cc, ro, co;
+  if (!img || stride < cols || spvo_oracle_crop_geometry(rows, cols, H, W, &cr, &cc, &ro, &co)) return -1;
+  std::vector<uint8_t> tmp((size_t)H * W);
+  resize_linear_8u(img + (size_t)ro * stride + co, cr, cc, stride, tmp.data(), H, W);
+  const float k = 1.0f / 255.0f;
+  if (input)
+    for (size_t i = 0; i < (size_t)H * W; ++i) input[i] = (float)tmp[i] * k;
+  if (resized) std::memcpy(resized, tmp.data(), tmp.size());
+  if (P) {
+    P[1 * 4 + 2] -= (float)ro;  // BASE:93 (only one of the two offsets is non-zero)
+    P[0 * 4 + 2] -= (float)co;  // BASE:109
+    const float r = (float)W / (float)cc;  // BASE:119
+    for (int i = 0; i < 8; ++i) P[i] *= r;  // rows 0 and 1
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -44,7 +44,7 @@ class StereoOut(C.Structure):
 # every symbol include/spvo_frontend.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
     "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
-    "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
+    "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
     "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch",
     "spvo_kernel_launches", "spvo_debug_counters", "spvo_profile_enable", "spvo_profile_num_kernels",
     "spvo_profile_kernel_name", "spvo_profile_read",
@@ -71,6 +71,8 @@ def load():
     L.spvo_set_stream.argtypes = [vp, vp]
     L.spvo_sync.argtypes = [vp]
     dec = [vp, vp, vp, ci, ci, ci, C.POINTER(DecodeCfg), vp, vp, vp, vp]
+    L.spvo_preprocess.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.spvo_preprocess_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
     L.spvo_decode.argtypes = dec
     L.spvo_decode_device.argtypes = dec
     mat = [vp, vp, ci, vp, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]

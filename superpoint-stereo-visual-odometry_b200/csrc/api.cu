@@ -126,7 +126,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
@@ -219,6 +219,79 @@ int spvo_decode(spvo_handle hh, const float* semi, const float* desc, int B, int
       CK(cudaMemcpyAsync(scores_out, h->st_scores, (size_t)B * K * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  return SPVO_OK;
+}
+
+// ---- preprocess (BASE:68-121, NN:139-161) ----
+static int check_preprocess_args(Handle* h, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                                 const void* input_out, const void* resized_out) {
+  if (!h) return SPVO_EINVAL;
+  if (B < 0 || rows <= 0 || cols <= 0 || stride < cols || H <= 0 || W <= 0)
+    return fail(h, SPVO_EINVAL, "preprocess: bad shape B=%d rows=%d cols=%d stride=%d H=%d W=%d", B, rows, cols, stride, H, W);
+  if (B > 0 && (!imgs || (!input_out && !resized_out))) return fail(h, SPVO_EINVAL, "preprocess: NULL buffer");
+  int cr, cc, ro, co;
+  if (!preprocess_geometry(rows, cols, H, W, &cr, &cc, &ro, &co))
+    return fail(h, SPVO_EINVAL, "preprocess: the %dx%d crop for a %dx%d network input is empty", cols, rows, W, H);
+  return SPVO_OK;
+}
+
+// BASE:93, 109, 119-120 on B host-side 3x4 row-major matrices
+static void patch_projection(float* proj, int B, int rows, int cols, int H, int W) {
+  int cr, cc, ro, co;
+  if (!proj || !preprocess_geometry(rows, cols, H, W, &cr, &cc, &ro, &co)) return;
+  const float r = static_cast<float>(W) / static_cast<float>(cc);
+  for (int b = 0; b < B; ++b) {
+    float* P = proj + (size_t)b * 12;
+    P[1 * 4 + 2] -= static_cast<float>(ro);
+    P[0 * 4 + 2] -= static_cast<float>(co);
+    for (int i = 0; i < 8; ++i) P[i] *= r;
+  }
+}
+
+int spvo_preprocess_device(spvo_handle hh, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                           float* input_out, uint8_t* resized_out, float* proj) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_preprocess_args(h, imgs, B, rows, cols, stride, H, W, input_out, resized_out);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  CK(launch_preprocess(h, imgs, B, rows, cols, stride, H, W, input_out, resized_out));
+  patch_projection(proj, B, rows, cols, H, W);
+  return SPVO_OK;
+}
+
+int spvo_preprocess(spvo_handle hh, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                    float* input_out, uint8_t* resized_out, float* proj) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  int rc = check_preprocess_args(h, imgs, B, rows, cols, stride, H, W, input_out, resized_out);
+  if (rc) return rc;
+  if (B == 0) return SPVO_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const size_t src_bytes = (size_t)B * rows * stride, px = (size_t)B * H * W;
+  if (h->pp_src_bytes < src_bytes) {
+    cudaFree(h->pp_src);
+    h->pp_src = nullptr;
+    h->pp_src_bytes = 0;
+    CK(cudaMalloc((void**)&h->pp_src, src_bytes));
+    h->pp_src_bytes = src_bytes;
+  }
+  if (h->pp_dst_px < px) {
+    cudaFree(h->pp_dst_f);
+    cudaFree(h->pp_dst_u8);
+    h->pp_dst_f = nullptr;
+    h->pp_dst_u8 = nullptr;
+    h->pp_dst_px = 0;
+    CK(cudaMalloc((void**)&h->pp_dst_f, px * sizeof(float)));
+    CK(cudaMalloc((void**)&h->pp_dst_u8, px));
+    h->pp_dst_px = px;
+  }
+  CK(cudaMemcpyAsync(h->pp_src, imgs, src_bytes, cudaMemcpyHostToDevice, st));
+  CK(launch_preprocess(h, h->pp_src, B, rows, cols, stride, H, W, input_out ? h->pp_dst_f : nullptr,
+                       resized_out ? h->pp_dst_u8 : nullptr));
+  if (input_out) CK(cudaMemcpyAsync(input_out, h->pp_dst_f, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (resized_out) CK(cudaMemcpyAsync(resized_out, h->pp_dst_u8, px, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  patch_projection(proj, B, rows, cols, H, W);
   return SPVO_OK;
 }
 
@@ -558,7 +631,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency", "k_carry_copy"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency", "k_carry_copy", "k_preprocess"};
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

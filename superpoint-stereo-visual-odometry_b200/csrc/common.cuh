@@ -24,7 +24,7 @@ struct Handle;
 // (spvo_profile_enable / spvo_profile_read: how bench.py measures the dominant kernel live).
 enum KernelId {
   KID_SOFTMAX_HEAT = 0, KID_DETECT, KID_SAMPLE_DESC, KID_DIST_EXACT, KID_ROW_SELECT, KID_COL_SELECT,
-  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_CONSISTENCY, KID_CARRY, KID_COUNT
+  KID_FINALIZE, KID_SETUP, KID_STEREO_FILTER, KID_TC_PREP, KID_TC_GEMM, KID_TC_RERANK, KID_TC_FALLBACK, KID_TC_FILL, KID_TC_TRIAGE, KID_DESC_PLANES, KID_DESC_NORM, KID_CONSISTENCY, KID_CARRY, KID_PREPROCESS, KID_COUNT
 };
 struct ProfRec {
   int kid;
@@ -62,6 +62,11 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
                             bool operands_ready = false);
 // Stereo pipeline: reserve max_batch image slots + 1 carry slot and return where decode should write.
 cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink);
+// preprocess.cu
+bool preprocess_geometry(int rows, int cols, int H, int W, int* crop_rows, int* crop_cols, int* row_off, int* col_off);
+cudaError_t launch_preprocess(Handle* h, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
+                              float* out_f, uint8_t* out_u8);
+
 // One device-to-device copy segment of k_carry_copy (sizes are multiples of 4 bytes).
 struct CopySeg {
   const void* src;
@@ -98,6 +103,10 @@ struct Handle {
   unsigned* nms_bitmap = nullptr; // [max_batch, max_h*ceil(max_w/32)] suppression bitmap of the multi-chunk path
   float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)
   int4* kp_par = nullptr;         // [max_batch, max_k] sampling parameters
+  uint8_t* pp_src = nullptr;      // host-form preprocess staging (grown on demand)
+  float* pp_dst_f = nullptr;
+  uint8_t* pp_dst_u8 = nullptr;
+  size_t pp_src_bytes = 0, pp_dst_px = 0;
   unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)
   // staging for the host-pointer entry points
   float* st_semi = nullptr;

@@ -93,6 +93,27 @@ class Frontend:
         return {self._L.spvo_profile_kernel_name(i).decode(): (float(ms[i]), int(cnt[i]))
                 for i in range(n) if cnt[i] > 0}
 
+    # ---- preprocess ---------------------------------------------------------------------------
+    def preprocess(self, imgs: np.ndarray, H: int, W: int, proj: Optional[np.ndarray] = None):
+        """Host-buffer preprocess (spvo_preprocess).  imgs [B,rows,cols] uint8 ->
+        (input [B,H,W] float32, resized [B,H,W] uint8, patched proj [B,3,4] or None)."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        B, rows, cols = imgs.shape
+        inp = np.empty((B, H, W), np.float32)
+        rs = np.empty((B, H, W), np.uint8)
+        P = None if proj is None else np.ascontiguousarray(proj, np.float32).reshape(B, 12).copy()
+        self._check(self._L.spvo_preprocess(self._h, _ptr(imgs), B, rows, cols, cols, H, W, _ptr(inp), _ptr(rs),
+                                            _ptr(P)))
+        return inp, rs, (None if P is None else P.reshape(B, 3, 4))
+
+    def preprocess_device(self, imgs, B, rows, cols, stride, H, W, input_out, resized_out=None, proj=None):
+        """Device-pointer preprocess (spvo_preprocess_device): torch CUDA tensors or raw pointers, async;
+        `proj` (numpy float32 [B,12], host) is patched in place."""
+        self._check(self._L.spvo_preprocess_device(self._h, _ptr(imgs), B, rows, cols, stride, H, W,
+                                                   _ptr(input_out), _ptr(resized_out), _ptr(proj)))
+
     # ---- decode -------------------------------------------------------------------------------
     def decode(self, semi: np.ndarray, desc: Optional[np.ndarray], conf_thresh=0.015, dist_thresh=4,
                border_remove=4, max_keypoints=1000, want_scores=True):
@@ -241,6 +262,8 @@ class SuperPointFeatureFrontEnd:
             self._mode = MATCH_NN_CROSSCHECK if cross_check else MATCH_NN
         # initPointers() (hpp:309-318): host I/O buffers the network writes into
         B, Hc, Wc = model_batch_size, self.output_height_, self.output_width_
+        self.input_data_ = np.zeros((B, input_height, input_width), np.float32)  # hpp:382
+        self.images_dq = collections.deque()                                       # hpp:123
         self.output_det_data_ = np.zeros((B, 65, Hc, Wc), np.float32)
         self.output_desc_data_ = np.zeros((B, 256, Hc, Wc), np.float32)
         self._fe = Frontend(device, B, input_height, input_width, max_keypoints)
@@ -254,6 +277,14 @@ class SuperPointFeatureFrontEnd:
         self.descriptors_dq.clear()
         self.cv_DMatches_list = [np.zeros(0, DMATCH_DTYPE) for _ in range(MATCH_TYPE_NUM)]
         self.maps_of_indices = [np.zeros(0, np.int32) for _ in range(MATCH_TYPE_NUM)]
+
+    def preprocessImage(self, img: np.ndarray, projection_matrix: np.ndarray, curr_batch: int):  # NN:139-161
+        """img: uint8 [rows, cols]; projection_matrix: float32 [3,4], patched in place (BASE:68-121)."""
+        assert curr_batch < self.model_batch_size_
+        inp, rs, P = self._fe.preprocess(img, self.input_height_, self.input_width_, projection_matrix)
+        projection_matrix[...] = P[0]
+        self.images_dq.append(rs[0])           # NN:153
+        self.input_data_[curr_batch] = inp[0]  # NN:159-160
 
     def postprocessDetectionAndDescription(self):  # NN:264-364
         r = self._fe.decode(self.output_det_data_, self.output_desc_data_, self.conf_thresh_, self.dist_thresh_,

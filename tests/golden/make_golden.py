@@ -3,6 +3,8 @@
 * match_cv2_*.npz   : inputs + outputs of the reference's real matcher, cv2.BFMatcher(NORM_L2)
                       (.match with / without crossCheck, .knnMatch(k=2) + the 0.8 ratio test of
                       feature_detection_base.cpp:466-472).  These PIN the matching oracle.
+* preprocess_cv2_*.npz : small seeded 8-bit images + the output of cv2.resize(INTER_LINEAR) on the crop the
+                      reference takes (feature_detection_base.cpp:68-121).  These PIN the preprocessing oracle.
 * decode_oracle_*.npz : seeded inputs (regenerated from the seed) + SHA-256 of the oracle's decode
                       outputs.  The reference's decode cannot be run here (Eigen/OpenCV C++/ROS/TensorRT
                       absent), so these pin the oracle against regressions, not against the reference.
@@ -69,6 +71,15 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"match_cv2_{i}.npz"), q=q, t=t, cv2_version=cv2.__version__,
                             **cv2_outputs(q, t))
     from oracle import oracle as O
+    # (rows, cols) -> (H, W): column crop + mild upscale (the KITTI case in small), row crop + downscale,
+    # exact 2x decimation (OpenCV's INTER_AREA shortcut), upscale 2.1x
+    for i, ((rows, cols), (H, W)) in enumerate([((47, 155), (48, 152)), ((120, 90), (24, 80)), ((64, 96), (32, 48)),
+                                                ((30, 41), (64, 88))]):
+        img = np.random.default_rng(500 + i).integers(0, 256, (rows, cols), dtype=np.uint8)
+        cr, cc, ro, co = O.crop_geometry(rows, cols, H, W)
+        ref = cv2.resize(img[ro:ro + cr, co:co + cc], (W, H), interpolation=cv2.INTER_LINEAR)
+        np.savez_compressed(os.path.join(HERE, f"preprocess_cv2_{i}.npz"), img=img, H=H, W=W, crop=(cr, cc, ro, co),
+                            resized=ref, cv2_version=cv2.__version__)
     for name, H, W, B, seed, sigma, K, conf, dist, border in DECODE_CASES:
         semi, desc = make_inputs(B, H, W, seed=seed, sigma=sigma)
         r = O.decode(semi, desc, conf_thresh=conf, dist_thresh=dist, border_remove=border, max_keypoints=K)
