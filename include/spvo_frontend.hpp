@@ -183,9 +183,31 @@ class SuperPointFeatureFrontEnd : public FeatureFrontEnd {
   }
 
   void initPointers() {  // HPP:309-318 (the Eigen thread pool has no equivalent: the work is on the GPU)
+    input_data_ = std::unique_ptr<float[]>(new float[(size_t)model_batch_size_ * input_height_ * input_width_]);
     output_det_data_ = std::unique_ptr<float[]>(new float[output_det_size_]);
     output_desc_data_ = std::unique_ptr<float[]>(new float[output_desc_size_]);
   }
+
+  // NN:139-161 + BASE:68-121.  img: rows x cols 8UC1 with `stride` bytes per row; projection_matrix: 3x4 row-major
+  // fp32, patched in place.  Writes slot curr_batch of input_data_ (the block runNeuralNetwork uploads, NN:164-166)
+  // and appends the resized 8-bit image to images_dq (NN:153).
+  void preprocessImage(const uint8_t* img, int rows, int cols, int stride, float* projection_matrix, int curr_batch) {
+    if (curr_batch < 0 || curr_batch >= model_batch_size_) throw Error(SPVO_EINVAL, "curr_batch out of range");
+    std::vector<uint8_t> resized((size_t)input_height_ * input_width_);
+    check(spvo_preprocess(handle_, img, 1, rows, cols, stride, input_height_, input_width_,
+                          input_data_.get() + (size_t)curr_batch * input_height_ * input_width_, resized.data(),
+                          projection_matrix));
+    images_dq.push_back(std::move(resized));
+    while (images_dq.size() > 4) images_dq.pop_front();
+  }
+#ifdef SPVO_HAVE_OPENCV
+  void preprocessImage(cv::Mat& img, cv::Mat& projection_matrix, const int curr_batch) {  // reference signature
+    if (img.type() != CV_8UC1 || projection_matrix.type() != CV_32FC1 || !projection_matrix.isContinuous())
+      throw Error(SPVO_EINVAL, "preprocessImage: 8UC1 image and continuous CV_32FC1 3x4 projection matrix expected");
+    preprocessImage(img.ptr<uint8_t>(), img.rows, img.cols, (int)img.step, projection_matrix.ptr<float>(), curr_batch);
+    img = cv::Mat(input_height_, input_width_, CV_8UC1, images_dq.back().data()).clone();
+  }
+#endif
 
   // NN:264-364.  Consumes output_det_data_ / output_desc_data_, appends model_batch_size_ entries to
   // keypoints_dq / descriptors_dq and trims the deques to 4 entries (NN:494-498).
@@ -215,6 +237,8 @@ class SuperPointFeatureFrontEnd : public FeatureFrontEnd {
   inline int getInputHeight() const { return input_height_; }
   inline int getInputWidth() const { return input_width_; }
 
+  std::unique_ptr<float[]> input_data_;             // [B,H,W] network input, HPP:382
+  std::deque<std::vector<uint8_t>> images_dq;      // resized 8-bit images, HPP:123 (cv::Mat in the reference)
   // host I/O buffers the network output is copied into (NN:170-176)
   std::unique_ptr<float[]> output_det_data_;   // [B,65,H/8,W/8]   HPP:383
   std::unique_ptr<float[]> output_desc_data_;  // [B,256,H/8,W/8]  HPP:384

@@ -2,6 +2,7 @@
 
   config 3  K = 2048, 1240x376, kNN-2 + 0.8 ratio test, 74 pairs per call           -> pairs/s
   config 4  640x192, K = 500, batch of ONE stereo pair, latency per call, plain launches and CUDA graph
+  preprocess  296 KITTI-sized 8-bit images -> network input (crop + resize + /255), device-resident
   config 5  matching only, N = M in {256 ... 8192}, cross-check and ratio modes, tensor path vs exact
             fp32 path (and cv2.BFMatcher on the host when importable, as the reference's matcher)
 
@@ -130,6 +131,28 @@ for N in (256, 512, 1024, 2048, 4096, 8192):
 out["config5_matching_sweep"] = sweep
 out["config5_note"] = ("single problem per call (latency-bound below N~2048: one problem fills few SMs); "
                        "bench.py's step runs 148 such problems per launch")
+fe.close()
+
+# ---------------- preprocess (the step before the network) ----------------
+rows, cols, H, W, B = 375, 1242, 376, 1240, 296
+imgs = torch.randint(0, 256, (3, B, rows, cols), dtype=torch.uint8, device=dev)  # ring of 3 batches (412 MB > L2)
+inp = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+rsz = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+fe = S.Frontend(0, 2, 64, 64, 16)
+fe.set_stream(stream.cuda_stream)
+i = [0]
+
+
+def stepp():
+    fe.preprocess_device(imgs[i[0] % 3], B, rows, cols, cols, H, W, inp, rsz, None)
+    i[0] += 1
+
+
+ms = timed(stepp, 30)
+alg_bytes = B * (rows * 1236 + H * W * 5)  # cropped 8-bit source read once + fp32 input and 8-bit image written
+out["preprocess_375x1242_to_376x1240"] = {"images_per_call": B, "ms_per_call": ms, "images_per_s": B / ms * 1e3,
+                                          "algorithmic_GBps": alg_bytes / (ms * 1e-3) / 1e9,
+                                          "note": "crop + cv::resize INTER_LINEAR (bit-exact) + /255; bytes = crop read + fp32 and u8 outputs"}
 fe.close()
 
 txt = json.dumps(out, indent=1)

@@ -126,7 +126,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};

@@ -107,6 +107,10 @@ struct Handle {
   float* pp_dst_f = nullptr;
   uint8_t* pp_dst_u8 = nullptr;
   size_t pp_src_bytes = 0, pp_dst_px = 0;
+  uint2* pp_tab = nullptr;        // resize coefficient tables [W + H] of the last geometry (pp_key)
+  size_t pp_tab_cap = 0;
+  int pp_key[4] = {-1, -1, -1, -1};
+  cudaStream_t pp_stream = nullptr;
   unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)
   // staging for the host-pointer entry points
   float* st_semi = nullptr;

@@ -17,7 +17,36 @@
 
 static void wr(FILE* f, const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) { perror("write"); exit(2); } }
 
+// usage 2: test_frontend_mirror --preprocess <in.bin> <out.bin>
+//   in.bin : int32 rows, cols, H, W ; 12 fp32 projection matrix ; rows*cols image bytes
+//   out.bin: input [H*W] fp32 (slot 1 of input_data_), resized [H*W] u8 (images_dq.back()), 12 fp32 patched matrix
+static int run_preprocess(const char* in, const char* out) {
+  FILE* fi = fopen(in, "rb");
+  FILE* fo = fopen(out, "wb");
+  int hdr[4];
+  float P[12];
+  if (!fi || !fo || fread(hdr, 4, 4, fi) != 4 || fread(P, 4, 12, fi) != 12) return 1;
+  const int rows = hdr[0], cols = hdr[1], H = hdr[2], W = hdr[3];
+  std::vector<uint8_t> img((size_t)rows * cols);
+  if (fread(img.data(), 1, img.size(), fi) != img.size()) return 1;
+  try {
+    spvo::SuperPointFeatureFrontEnd fe(spvo::MatcherType::BF, spvo::SelectorType::NN, true, 2, H, W, 0.015f, 4, 4, 2.0f,
+                                       0.25f, 100, 0);
+    fe.preprocessImage(img.data(), rows, cols, cols, P, 1);  // NN:482: the right image goes to batch slot 1
+    wr(fo, fe.input_data_.get() + (size_t)H * W, (size_t)H * W * 4);
+    wr(fo, fe.images_dq.back().data(), (size_t)H * W);
+    wr(fo, P, sizeof(P));
+  } catch (const spvo::Error& e) {
+    fprintf(stderr, "spvo error %d: %s\n", e.code, e.what());
+    return 4;
+  }
+  fclose(fo);
+  fclose(fi);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && std::string(argv[1]) == "--preprocess") return run_preprocess(argv[2], argv[3]);
   if (argc < 5) return 1;
   FILE* fi = fopen(argv[1], "rb");
   FILE* fo = fopen(argv[2], "wb");

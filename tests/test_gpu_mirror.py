@@ -94,3 +94,26 @@ def test_python_mirror_class(oracle, spvo):
             assert (fe.cv_DMatches_list[spvo.CURR_LEFT_PREV_LEFT] == mt).all()
             assert (fe.maps_of_indices[spvo.PREV_LEFT_PREV_RIGHT] == ref[f - 1][2]).all()   # BASE:475-481
         assert len(fe.keypoints_dq) <= 4
+
+
+def test_cpp_mirror_preprocess_image(oracle, spvo, tmp_path):
+    """spvo::SuperPointFeatureFrontEnd::preprocessImage (NN:139-161) through the C++ mirror vs the oracle."""
+    if not os.path.exists(BIN):
+        import __graft_entry__ as g
+        g.build()
+    rows, cols, H, W = 370, 1226, 120, 392
+    img = np.random.default_rng(9).integers(0, 256, (rows, cols), dtype=np.uint8)
+    P = np.array([707.09, 0, 601.89, -379.8, 0, 707.09, 183.11, 0, 0, 0, 1, 0], np.float32)
+    fin, fout = tmp_path / "pin.bin", tmp_path / "pout.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("4i", rows, cols, H, W))
+        f.write(P.tobytes())
+        f.write(img.tobytes())
+    subprocess.run([BIN, "--preprocess", str(fin), str(fout)], check=True, timeout=120)
+    buf = open(fout, "rb").read()
+    inp = np.frombuffer(buf, np.float32, H * W).reshape(H, W)
+    rs = np.frombuffer(buf, np.uint8, H * W, H * W * 4).reshape(H, W)
+    Pp = np.frombuffer(buf, np.float32, 12, H * W * 5).reshape(3, 4)
+    oi, ors, oP = oracle.preprocess(img, H, W, P)
+    assert (rs == ors).all() and (inp.view(np.uint32) == oi.view(np.uint32)).all()
+    assert (Pp.view(np.uint32) == oP.view(np.uint32)).all()
