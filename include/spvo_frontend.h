@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPVO_ABI_VERSION 2
+#define SPVO_ABI_VERSION 3
 
 #define SPVO_DESC_DIM 256      /* output_desc_channel_, HPP:359 */
 #define SPVO_DET_CHANNELS 65   /* output_det_channel_,  HPP:355 */
@@ -220,6 +220,21 @@ int spvo_stereo_batch_device(spvo_handle h, const float* semi, const float* desc
  * Pinned host memory gives full PCIe rate. */
 int spvo_stereo_batch(spvo_handle h, const float* semi, const float* desc, int F, int H, int W,
                       const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
+
+/* ---- fp16 network outputs (staging straight from an fp16 inference engine).  Same functions, same
+ * results contract, but semi / desc hold IEEE binary16 elements in the same NCHW layout.  fp16 -> fp32 is exact, so
+ * the outputs are bit-identical to the fp32 entry points fed with the widened tensors; decode's HBM traffic (and the
+ * host forms' H2D) halves. ---- */
+int spvo_decode_f16(spvo_handle h, const void* semi_f16, const void* desc_f16, int B, int H, int W,
+                    const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                    float* scores_out);
+int spvo_decode_device_f16(spvo_handle h, const void* semi_f16, const void* desc_f16, int B, int H, int W,
+                           const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                           float* scores_out);
+int spvo_stereo_batch_f16(spvo_handle h, const void* semi_f16, const void* desc_f16, int F, int H, int W,
+                          const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
+int spvo_stereo_batch_device_f16(spvo_handle h, const void* semi_f16, const void* desc_f16, int F, int H, int W,
+                                 const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
 
 /* ---- introspection for tests / bench ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

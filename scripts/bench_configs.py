@@ -133,6 +133,53 @@ out["config5_note"] = ("single problem per call (latency-bound below N~2048: one
                        "bench.py's step runs 148 such problems per launch")
 fe.close()
 
+# ---------------- fp16 network outputs (bench.py's workload, inputs as binary16) ----------------
+H, W, K, F = 376, 1240, 1000, 148
+semi, desc = synth.make_stream(2 * F, H, W, seed=0, device=dev)
+semi = semi.view(2, F, 2, 65, H // 8, W // 8)
+desc = desc.view(2, F, 2, 256, H // 8, W // 8)
+s16, d16 = semi.half(), desc.half()
+fe = S.Frontend(0, 2 * F, H, W, K)
+fe.set_stream(stream.cuda_stream)
+o = fe.alloc_stereo_out(F, K, device=dev)
+i = [0]
+
+
+def step16():
+    fe.stereo_batch_device(s16[i[0] % 2], d16[i[0] % 2], F, H, W, o, max_keypoints=K, f16=True)
+    i[0] += 1
+
+
+def step32():
+    fe.stereo_batch_device(semi[i[0] % 2], desc[i[0] % 2], F, H, W, o, max_keypoints=K)
+    i[0] += 1
+
+
+ms32 = timed(step32, 12)
+fe.profile_enable(True)
+ms16 = timed(step16, 12)
+prof = fe.profile_read()
+fe.profile_enable(False)
+hs, hd = s16[0].cpu().pin_memory(), d16[0].cpu().pin_memory()
+ho = fe.alloc_stereo_out(F, K, device="cpu", pinned=True)
+fe.set_stream(0)
+for _ in range(2):
+    fe.stereo_batch(hs, hd, F, H, W, ho, max_keypoints=K, f16=True)
+t0 = time.perf_counter()
+for _ in range(5):
+    fe.stereo_batch(hs, hd, F, H, W, ho, max_keypoints=K, f16=True)
+e2e16 = 5 * F / (time.perf_counter() - t0)
+out["fp16_inputs_148_pairs"] = {"ms_per_step_f16": ms16, "pairs_per_s_f16": F / ms16 * 1e3, "ms_per_step_f32_same_run": ms32,
+                                "e2e_pairs_per_s_f16_host_buffers": e2e16,
+                                "kernels_ms_f16": {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]},
+                                "note": "spvo_stereo_batch[_device]_f16: same results as the widened fp32 tensors; "
+                                        "decode reads half the bytes, the host form moves half the bytes over PCIe"}
+fe.close()
+del semi, desc, s16, d16, o
+torch.cuda.synchronize()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+
 # ---------------- preprocess (the step before the network) ----------------
 rows, cols, H, W, B = 375, 1242, 376, 1240, 296
 imgs = torch.randint(0, 256, (3, B, rows, cols), dtype=torch.uint8, device=dev)  # ring of 3 batches (412 MB > L2)

@@ -46,6 +46,7 @@ SYMBOLS = [
     "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
     "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
     "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch",
+    "spvo_decode_f16", "spvo_decode_device_f16", "spvo_stereo_batch_f16", "spvo_stereo_batch_device_f16",
     "spvo_kernel_launches", "spvo_debug_counters", "spvo_profile_enable", "spvo_profile_num_kernels",
     "spvo_profile_kernel_name", "spvo_profile_read",
 ]
@@ -75,6 +76,8 @@ def load():
     L.spvo_preprocess_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
     L.spvo_decode.argtypes = dec
     L.spvo_decode_device.argtypes = dec
+    L.spvo_decode_f16.argtypes = dec
+    L.spvo_decode_device_f16.argtypes = dec
     mat = [vp, vp, ci, vp, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
     L.spvo_match.argtypes = mat
     L.spvo_match_device.argtypes = mat
@@ -84,6 +87,8 @@ def load():
     ster = [vp, vp, vp, ci, ci, ci, C.POINTER(StereoCfg), C.POINTER(StereoOut)]
     L.spvo_stereo_batch_device.argtypes = ster
     L.spvo_stereo_batch.argtypes = ster
+    L.spvo_stereo_batch_f16.argtypes = ster
+    L.spvo_stereo_batch_device_f16.argtypes = ster
     L.spvo_kernel_launches.restype = C.c_longlong
     L.spvo_kernel_launches.argtypes = [vp]
     L.spvo_debug_counters.argtypes = [vp, vp, ci]

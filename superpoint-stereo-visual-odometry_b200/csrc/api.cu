@@ -165,7 +165,7 @@ int spvo_sync(spvo_handle hh) {
   return SPVO_OK;
 }
 
-static int check_decode_args(Handle* h, const float* semi, int B, int H, int W, const spvo_decode_cfg* cfg,
+static int check_decode_args(Handle* h, const void* semi, int B, int H, int W, const spvo_decode_cfg* cfg,
                              spvo_keypoint* kpts, int* n_out) {
   if (!h) return SPVO_EINVAL;
   if (!semi || !cfg || !kpts || !n_out) return fail(h, SPVO_EINVAL, "decode: NULL argument");
@@ -183,32 +183,43 @@ static int check_decode_args(Handle* h, const float* semi, int B, int H, int W, 
   return SPVO_OK;
 }
 
-int spvo_decode_device(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
-                       const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
-                       float* scores_out) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
+static int decode_device_impl(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
+                              const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                              float* scores_out) {
   int rc = check_decode_args(h, semi, B, H, W, cfg, kpts_out, n_out);
   if (rc) return rc;
   DeviceGuard g(h->device);
-  CK(launch_decode(h, semi, desc, B, H, W, *cfg, kpts_out, desc_out, n_out, scores_out));
+  CK(launch_decode(h, semi, desc, in_f16, B, H, W, *cfg, kpts_out, desc_out, n_out, scores_out));
   return SPVO_OK;
 }
 
-int spvo_decode(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
-                const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
-                float* scores_out) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
+int spvo_decode_device(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
+                       const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                       float* scores_out) {
+  return decode_device_impl(reinterpret_cast<Handle*>(hh), semi, desc, 0, B, H, W, cfg, kpts_out, desc_out, n_out,
+                            scores_out);
+}
+
+int spvo_decode_device_f16(spvo_handle hh, const void* semi, const void* desc, int B, int H, int W,
+                           const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                           float* scores_out) {
+  return decode_device_impl(reinterpret_cast<Handle*>(hh), semi, desc, 1, B, H, W, cfg, kpts_out, desc_out, n_out,
+                            scores_out);
+}
+
+static int decode_host_impl(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
+                            const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                            float* scores_out) {
   int rc = check_decode_args(h, semi, B, H, W, cfg, kpts_out, n_out);
   if (rc) return rc;
   if (B == 0) return SPVO_OK;
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
-  const size_t cells = (size_t)(H / 8) * (W / 8), K = cfg->max_keypoints;
+  const size_t cells = (size_t)(H / 8) * (W / 8), K = cfg->max_keypoints, esz = in_f16 ? 2 : 4;
   const bool with_desc = desc && desc_out;
-  CK(cudaMemcpyAsync(h->st_semi, semi, (size_t)B * 65 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (with_desc)
-    CK(cudaMemcpyAsync(h->st_desc, desc, (size_t)B * 256 * cells * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(launch_decode(h, h->st_semi, with_desc ? h->st_desc : nullptr, B, H, W, *cfg, h->st_kpts,
+  CK(cudaMemcpyAsync(h->st_semi, semi, (size_t)B * 65 * cells * esz, cudaMemcpyHostToDevice, st));
+  if (with_desc) CK(cudaMemcpyAsync(h->st_desc, desc, (size_t)B * 256 * cells * esz, cudaMemcpyHostToDevice, st));
+  CK(launch_decode(h, h->st_semi, with_desc ? h->st_desc : nullptr, in_f16, B, H, W, *cfg, h->st_kpts,
                    with_desc ? h->st_desc_out : nullptr, h->st_n, scores_out ? h->st_scores : nullptr));
   CK(cudaMemcpyAsync(n_out, h->st_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (K > 0) {
@@ -220,6 +231,20 @@ int spvo_decode(spvo_handle hh, const float* semi, const float* desc, int B, int
   }
   CK(cudaStreamSynchronize(st));
   return SPVO_OK;
+}
+
+int spvo_decode(spvo_handle hh, const float* semi, const float* desc, int B, int H, int W,
+                const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                float* scores_out) {
+  return decode_host_impl(reinterpret_cast<Handle*>(hh), semi, desc, 0, B, H, W, cfg, kpts_out, desc_out, n_out,
+                          scores_out);
+}
+
+int spvo_decode_f16(spvo_handle hh, const void* semi, const void* desc, int B, int H, int W,
+                    const spvo_decode_cfg* cfg, spvo_keypoint* kpts_out, float* desc_out, int* n_out,
+                    float* scores_out) {
+  return decode_host_impl(reinterpret_cast<Handle*>(hh), semi, desc, 1, B, H, W, cfg, kpts_out, desc_out, n_out,
+                          scores_out);
 }
 
 // ---- preprocess (BASE:68-121, NN:139-161) ----
@@ -424,7 +449,7 @@ int spvo_stereo_reset(spvo_handle hh) {
   return SPVO_OK;
 }
 
-static int check_stereo_args(Handle* h, const float* semi, const float* desc, int F, int H, int W,
+static int check_stereo_args(Handle* h, const void* semi, const void* desc, int F, int H, int W,
                              const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
   if (!h) return SPVO_EINVAL;
   if (!cfg || !out || !desc) return fail(h, SPVO_EINVAL, "stereo_batch: NULL argument");
@@ -482,7 +507,7 @@ __global__ void __launch_bounds__(256) k_carry_copy(const CopyList L) {
   }
 }
 
-static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int F, int H, int W,
+static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in_f16, int F, int H, int W,
                            const spvo_stereo_cfg* cfg, spvo_keypoint* kpts, float* desc_out, int* n_kpts,
                            spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep, spvo_quad* quads,
                            int* n_quads) {
@@ -496,7 +521,8 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   const int carry_slot = h->max_batch;
   TcSink sink;
   if (tensor) CK(tc_prepare_slots(h, h->max_batch + 1, h->max_k, 2 * h->max_batch, &sink));
-  CK(launch_decode(h, semi, desc, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr, tensor ? &sink : nullptr));
+  CK(launch_decode(h, semi, desc, in_f16, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr,
+                   tensor ? &sink : nullptr));
   if (2 * F > h->probs_cap) {
     cudaFree(h->probs);
     h->probs = nullptr;
@@ -534,21 +560,34 @@ static int stereo_pipeline(Handle* h, const float* semi, const float* desc, int 
   return SPVO_OK;
 }
 
-int spvo_stereo_batch_device(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
-                             const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
+static int stereo_batch_device_impl(Handle* h, const void* semi, const void* desc, int in_f16, int F, int H, int W,
+                                    const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
   int rc = check_stereo_args(h, semi, desc, F, H, W, cfg, out);
   if (rc) return rc;
   if (!out->desc) return fail(h, SPVO_EINVAL, "stereo_batch_device: desc output is required");
   if (F == 0) return SPVO_OK;
   DeviceGuard g(h->device);
-  return stereo_pipeline(h, semi, desc, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
+  return stereo_pipeline(h, semi, desc, in_f16, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
                          out->n_matches, out->q2t, out->stereo_keep, out->quads, out->n_quads);
 }
 
-int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
-                      const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
+int spvo_stereo_batch_device(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
+                             const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  return stereo_batch_device_impl(reinterpret_cast<Handle*>(hh), semi, desc, 0, F, H, W, cfg, out);
+}
+
+int spvo_stereo_batch_device_f16(spvo_handle hh, const void* semi, const void* desc, int F, int H, int W,
+                                 const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  return stereo_batch_device_impl(reinterpret_cast<Handle*>(hh), semi, desc, 1, F, H, W, cfg, out);
+}
+
+static int stereo_batch_host_impl(Handle* h, const void* semi_v, const void* desc_v, int in_f16, int F, int H, int W,
+                                  const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  const unsigned char* semi = static_cast<const unsigned char*>(semi_v);
+  const unsigned char* desc = static_cast<const unsigned char*>(desc_v);
+  const size_t esz = in_f16 ? 2 : 4;
+  unsigned char* st_semi = reinterpret_cast<unsigned char*>(h ? h->st_semi : nullptr);
+  unsigned char* st_desc = reinterpret_cast<unsigned char*>(h ? h->st_desc : nullptr);
   int rc = check_stereo_args(h, semi, desc, F, H, W, cfg, out);
   if (rc) return rc;
   if (F == 0) return SPVO_OK;
@@ -577,9 +616,9 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
   CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[4], 0));
   for (int c = 0; c < nchunk; ++c) {
     const size_t f0 = (size_t)F * c / nchunk, f1 = (size_t)F * (c + 1) / nchunk, nb = 2 * (f1 - f0);
-    CK(cudaMemcpyAsync(h->st_semi + 2 * f0 * 65 * cells, semi + 2 * f0 * 65 * cells, nb * 65 * cells * sizeof(float),
+    CK(cudaMemcpyAsync(st_semi + 2 * f0 * 65 * cells * esz, semi + 2 * f0 * 65 * cells * esz, nb * 65 * cells * esz,
                        cudaMemcpyHostToDevice, h->copy_stream));
-    CK(cudaMemcpyAsync(h->st_desc + 2 * f0 * 256 * cells, desc + 2 * f0 * 256 * cells, nb * 256 * cells * sizeof(float),
+    CK(cudaMemcpyAsync(st_desc + 2 * f0 * 256 * cells * esz, desc + 2 * f0 * 256 * cells * esz, nb * 256 * cells * esz,
                        cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(h->copy_ev[c], h->copy_stream));
   }
@@ -596,7 +635,8 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
     uint8_t* d_keep = h->st_skeep + f0 * K;
     spvo_quad* d_quads = h->st_quads + f0 * K;
     int* d_nq = h->st_nquads + f0;
-    rc = stereo_pipeline(h, h->st_semi + 2 * f0 * 65 * cells, h->st_desc + 2 * f0 * 256 * cells, (int)Fc, H, W, cfg, d_kp,
+    rc = stereo_pipeline(h, st_semi + 2 * f0 * 65 * cells * esz, st_desc + 2 * f0 * 256 * cells * esz, in_f16, (int)Fc, H, W,
+                         cfg, d_kp,
                          d_desc, d_n, d_m, d_nm, d_q2t, out->stereo_keep ? d_keep : nullptr,
                          out->quads ? d_quads : nullptr, d_nq);
     if (rc) return rc;
@@ -621,6 +661,16 @@ int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int 
   }
   CK(cudaStreamSynchronize(st));
   return SPVO_OK;
+}
+
+int spvo_stereo_batch(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
+                      const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  return stereo_batch_host_impl(reinterpret_cast<Handle*>(hh), semi, desc, 0, F, H, W, cfg, out);
+}
+
+int spvo_stereo_batch_f16(spvo_handle hh, const void* semi, const void* desc, int F, int H, int W,
+                          const spvo_stereo_cfg* cfg, const spvo_stereo_out* out) {
+  return stereo_batch_host_impl(reinterpret_cast<Handle*>(hh), semi, desc, 1, F, H, W, cfg, out);
 }
 
 long long spvo_kernel_launches(spvo_handle hh) {

@@ -50,7 +50,8 @@ struct TcSink {
 };
 
 // ---- decode.cu ----
-cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
+// semi / desc: fp32 (in_f16 = 0) or fp16 (in_f16 = 1) device tensors
+cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
                           float* scores, const TcSink* sink = nullptr);
 // ---- match.cu ----

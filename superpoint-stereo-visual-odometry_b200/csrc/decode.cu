@@ -21,6 +21,13 @@
 
 namespace spvo {
 
+// Network outputs arrive as fp32 (the reference's layout, HPP:382-384) or as fp16 (an fp16 TensorRT engine's
+// bindings).  fp16 -> fp32 is exact, so everything downstream is the same arithmetic on the same values.
+__device__ __forceinline__ float ld_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_in(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
 // ------------------------------------------------------------------------------------------------
 // K1: softmax + heatmap.  One THREAD per 8x8 cell, 128 consecutive cells per block.
 //   * every global load is one 128 B coalesced request per warp (a channel plane, 32 consecutive cells); all 65
@@ -31,18 +38,19 @@ namespace spvo {
 //     contiguous.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHeatThreads = 128;
+template <typename T>
 __global__ void __launch_bounds__(kHeatThreads, 4)
-k_softmax_heat(const float* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
+k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
                uint2* __restrict__ cellmax, int Hc, int Wc, float conf) {
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
   if (cell >= cells) return;
-  const float* src = semi + (size_t)b * 65 * cells + cell;
+  const T* src = semi + (size_t)b * 65 * cells + cell;
   float e[64];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) e[c] = __ldg(src + (size_t)c * cells);
-  const float xd = __ldg(src + (size_t)64 * cells);
+  for (int c = 0; c < 64; ++c) e[c] = ld_in(src + (size_t)c * cells);
+  const float xd = ld_in(src + (size_t)64 * cells);
   float s = 0.0f;
 #pragma unroll
   for (int c = 0; c < 64; ++c) {
@@ -739,8 +747,9 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
 // right, unfused; squared norm = per-lane partial sums over ascending channels, xor butterfly
 // 16,8,4,2,1; true division by sqrt.
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ kpts, const int* __restrict__ n_out,
+k_sample_desc(const T* __restrict__ desc, const spvo_keypoint* __restrict__ kpts, const int* __restrict__ n_out,
               float* __restrict__ out, int H, int W, int K) {
   const int b = blockIdx.y;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -763,19 +772,19 @@ k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ 
   const float cr = __fsub_rn(1.0f, __fsub_rn(c8, (float)c0));
   const float irr = __fsub_rn(1.0f, rr), icr = __fsub_rn(1.0f, cr);
   const int r1 = min(r0 + 1, Hc - 1), c1 = min(c0 + 1, Wc - 1);
-  const float* base = desc + (size_t)b * 256 * cells;
-  const float* tl = base + (size_t)r0 * Wc + c0;
-  const float* tr = base + (size_t)r0 * Wc + c1;
-  const float* bl = base + (size_t)r1 * Wc + c0;
-  const float* br = base + (size_t)r1 * Wc + c1;
+  const T* base = desc + (size_t)b * 256 * cells;
+  const T* tl = base + (size_t)r0 * Wc + c0;
+  const T* tr = base + (size_t)r0 * Wc + c1;
+  const T* bl = base + (size_t)r1 * Wc + c0;
+  const T* br = base + (size_t)r1 * Wc + c1;
   float a[8], bq[8], c[8], dd[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const size_t off = (size_t)(lane + 32 * i) * cells;
-    a[i] = __ldg(tl + off);
-    bq[i] = __ldg(tr + off);
-    c[i] = __ldg(bl + off);
-    dd[i] = __ldg(br + off);
+    a[i] = ld_in(tl + off);
+    bq[i] = ld_in(tr + off);
+    c[i] = ld_in(bl + off);
+    dd[i] = ld_in(br + off);
   }
   float v[8], part = 0.0f;
 #pragma unroll
@@ -810,36 +819,59 @@ k_sample_desc(const float* __restrict__ desc, const spvo_keypoint* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kCP = 2;  // channel planes per CTA: 2 x 29 KB at 1240x376 -> 3 CTAs per SM (1 plane/CTA measured the same)
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, const int* __restrict__ n_out,
+k_desc_planes(const T* __restrict__ desc, const int4* __restrict__ kp_par, const int* __restrict__ n_out,
               float* __restrict__ tmp, int cells, int K, int plane_pitch, int Kp) {
-  extern __shared__ __align__(16) float sp[];  // kCP planes, each plane_pitch floats
+  extern __shared__ __align__(16) unsigned char sp_raw[];  // kCP planes, each plane_pitch elements of T
+  T* sp = reinterpret_cast<T*>(sp_raw);
   const int b = blockIdx.y, cg = blockIdx.x;
   const int n = n_out[b];
   if (n == 0) return;
+  constexpr int kPer16 = 16 / (int)sizeof(T);  // elements per 16-byte cp.async
   int mis[kCP];
 #pragma unroll
   for (int c = 0; c < kCP; ++c) {
-    const float* src = desc + ((size_t)b * 256 + (size_t)cg * kCP + c) * cells;
+    const T* src = desc + ((size_t)b * 256 + (size_t)cg * kCP + c) * cells;
     // keep the 16-byte phase of the global address so the body can use 16-byte cp.async
-    const int m = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const int m = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(T)) & (kPer16 - 1));
     mis[c] = m;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sp + (size_t)c * plane_pitch + m);
-    const int head = min((4 - m) & 3, cells);
-    const int body4 = (cells - head) >> 2;
-    const int tail0 = head + body4 * 4;
-    if (threadIdx.x < head) cp_async4(dst + threadIdx.x * 4, src + threadIdx.x);
-    for (int i = threadIdx.x; i < body4; i += 256) cp_async16(dst + (head + 4 * i) * 4, src + head + 4 * i);
-    if (threadIdx.x < cells - tail0) cp_async4(dst + (tail0 + threadIdx.x) * 4, src + tail0 + threadIdx.x);
+    T* dstp = sp + (size_t)c * plane_pitch + m;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dstp);
+    const int head = min((kPer16 - m) & (kPer16 - 1), cells);
+    const int body = (cells - head) / kPer16;
+    const int tail0 = head + body * kPer16;
+    if (sizeof(T) == 4) {  // 4-byte elements: head / tail are asynchronous 4-byte copies
+      if (threadIdx.x < head) cp_async4(dst + threadIdx.x * 4, src + threadIdx.x);
+    }
+    for (int i = threadIdx.x; i < body; i += 256)
+      cp_async16(dst + (head + kPer16 * i) * (int)sizeof(T), src + head + kPer16 * i);
+    if (sizeof(T) == 4) {
+      if (threadIdx.x < cells - tail0) cp_async4(dst + (tail0 + threadIdx.x) * 4, src + tail0 + threadIdx.x);
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // 2-byte elements (cp.async moves 4 / 8 / 16 bytes): warp c loads plane c's < 8 head / tail elements into
+  // registers now and stores them after the wait below, so that their latency hides behind the asynchronous body
+  const int hw = threadIdx.x >> 5, ht = threadIdx.x & 31;
+  T hv = T(), tv = T();
+  int h_idx = -1, t_idx = -1, hm = 0;
+  if (sizeof(T) != 4 && hw < kCP) {
+    const T* src = desc + ((size_t)b * 256 + (size_t)cg * kCP + hw) * cells;
+    hm = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(T)) & (kPer16 - 1));
+    const int head = min((kPer16 - hm) & (kPer16 - 1), cells);
+    const int tail0 = head + (cells - head) / kPer16 * kPer16;
+    if (ht < head) { h_idx = ht; hv = src[ht]; }
+    if (ht < cells - tail0) { t_idx = tail0 + ht; tv = src[tail0 + ht]; }
+  }
   // the sampling parameters of this thread's keypoints travel while the planes are in flight
   constexpr int kPre = 4;
   int4 pre[kPre];
@@ -849,6 +881,11 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
     pre[i] = k < n ? __ldg(kp_par + (size_t)b * K + k) : make_int4(0, 0, 0, 0);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (sizeof(T) != 4 && hw < kCP) {
+    T* dstp = sp + (size_t)hw * plane_pitch + hm;
+    if (h_idx >= 0) dstp[h_idx] = hv;
+    if (t_idx >= 0) dstp[t_idx] = tv;
+  }
   __syncthreads();
 #pragma unroll 1
   for (int k0 = 0; k0 < n; k0 += 256 * kPre) {
@@ -862,11 +899,11 @@ k_desc_planes(const float* __restrict__ desc, const int4* __restrict__ kp_par, c
     const float irr = __fsub_rn(1.0f, rr), icr = __fsub_rn(1.0f, cr);
 #pragma unroll
     for (int c = 0; c < kCP; ++c) {
-      const float* pl = sp + (size_t)c * plane_pitch + mis[c];
-      const float t1 = __fmul_rn(__fmul_rn(pl[o_tl], rr), cr);
-      const float t2 = __fmul_rn(__fmul_rn(pl[o_tl + dc], rr), icr);
-      const float t3 = __fmul_rn(__fmul_rn(pl[o_tl + dr], irr), cr);
-      const float t4 = __fmul_rn(__fmul_rn(pl[o_tl + dr + dc], irr), icr);
+      const T* pl = sp + (size_t)c * plane_pitch + mis[c];
+      const float t1 = __fmul_rn(__fmul_rn(to_f32(pl[o_tl]), rr), cr);
+      const float t2 = __fmul_rn(__fmul_rn(to_f32(pl[o_tl + dc]), rr), icr);
+      const float t3 = __fmul_rn(__fmul_rn(to_f32(pl[o_tl + dr]), irr), cr);
+      const float t4 = __fmul_rn(__fmul_rn(to_f32(pl[o_tl + dr + dc]), irr), icr);
       tmp[((size_t)b * 256 + (size_t)cg * kCP + c) * Kp + k] = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
     }
   }
@@ -963,14 +1000,16 @@ static size_t detect_smem_bytes(int H, int W, int K, int cap) {
 }
 
 // One contiguous range of images [b0, b0 + B) on the handle's CURRENT stream (h->stream).
-static cudaError_t launch_decode_range(Handle* h, const float* semi, const float* desc, int b0, int B, int H, int W,
+static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void* desc_v, int in_f16, int b0, int B,
+                                       int H, int W,
                                        const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
                                        float* scores, const TcSink* sink) {
   cudaStream_t st = h->stream;
   const int Hc = H / 8, Wc = W / 8, cells = Hc * Wc, K = cfg.max_keypoints;
   cudaError_t e;
-  semi += (size_t)b0 * 65 * cells;
-  if (desc) desc += (size_t)b0 * 256 * cells;
+  const size_t esz = in_f16 ? sizeof(__half) : sizeof(float);
+  const unsigned char* semi = static_cast<const unsigned char*>(semi_v) + (size_t)b0 * 65 * cells * esz;
+  const unsigned char* desc = desc_v ? static_cast<const unsigned char*>(desc_v) + (size_t)b0 * 256 * cells * esz : nullptr;
   kpts += (size_t)b0 * K;
   if (desc_out) desc_out += (size_t)b0 * K * 256;
   n_out += b0;
@@ -982,15 +1021,21 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
   dim3 g1((cells + kHeatThreads - 1) / kHeatThreads, B);
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
-    k_softmax_heat<<<g1, kHeatThreads, 0, st>>>(semi, heat, hist, cellmax, Hc, Wc, cfg.conf_thresh);
+    if (in_f16)
+      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, hist, cellmax, Hc,
+                                                          Wc, cfg.conf_thresh);
+    else
+      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, hist, cellmax, Hc,
+                                                         Wc, cfg.conf_thresh);
   }
   if (K > 0) {
     DetectParams p;
     p.heat = heat; p.cellmax = cellmax; p.hist = hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
-    const int plane_pitch = (cells + 4 + 3) & ~3;
-    const size_t smem_planes = (size_t)kCP * plane_pitch * sizeof(float);
+    const int per16 = (int)(16 / esz);  // one 16-byte unit of slack for the address phase, pitch in whole units
+    const int plane_pitch = (cells + per16 + per16 - 1) & ~(per16 - 1);
+    const size_t smem_planes = (size_t)kCP * plane_pitch * esz;
     const bool streaming = desc && desc_out && h->desc_tmp && h->kp_par && smem_planes <= 200 * 1024;
     int4* kp_par = streaming ? h->kp_par + (size_t)b0 * K : nullptr;
     const int Kp = (K + 3) & ~3;  // scratch pitch: 16-byte loads in k_desc_normalize
@@ -1009,7 +1054,9 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
       k_detect<<<B, kDetectThreads, smem, st>>>(p);
     }
     if (streaming) {
-      if ((e = cudaFuncSetAttribute(k_desc_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
+      if ((e = cudaFuncSetAttribute(k_desc_planes<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
+        return e;
+      if ((e = cudaFuncSetAttribute(k_desc_planes<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
         return e;
       TcSink sk;
       if (sink) {
@@ -1028,9 +1075,14 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
         const int gb = min(grp, B - g0);
         {
           LaunchScope ls(h, KID_DESC_PLANES);
-          k_desc_planes<<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(desc + (size_t)g0 * 256 * cells,
-                                                                       kp_par + (size_t)g0 * K, n_out + g0,
-                                                                       tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
+          if (in_f16)
+            k_desc_planes<__half><<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(
+                reinterpret_cast<const __half*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K, n_out + g0,
+                tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
+          else
+            k_desc_planes<float><<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(
+                reinterpret_cast<const float*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K, n_out + g0,
+                tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
         }
         TcSink sg = sk;
         if (sg.xb) {
@@ -1045,7 +1097,10 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
     } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);
       LaunchScope ls(h, KID_SAMPLE_DESC);
-      k_sample_desc<<<g3, 256, 0, st>>>(desc, kpts, n_out, desc_out, H, W, K);
+      if (in_f16)
+        k_sample_desc<__half><<<g3, 256, 0, st>>>(reinterpret_cast<const __half*>(desc), kpts, n_out, desc_out, H, W, K);
+      else
+        k_sample_desc<float><<<g3, 256, 0, st>>>(reinterpret_cast<const float*>(desc), kpts, n_out, desc_out, H, W, K);
     }
   } else {
     if ((e = cudaMemsetAsync(n_out, 0, (size_t)B * sizeof(int), st)) != cudaSuccess) return e;
@@ -1056,14 +1111,14 @@ static cudaError_t launch_decode_range(Handle* h, const float* semi, const float
 // Large batches are decoded as sub-batches alternating over two auxiliary streams: the intermediates of a
 // sub-batch (heatmap, un-normalised descriptors) then stay L2-resident between its kernels, and the
 // latency-bound per-image k_detect of one sub-batch overlaps the bandwidth-bound kernels of the other.
-cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B, int H, int W,
+cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
                           float* scores, const TcSink* sink) {
   if (B == 0) return cudaSuccess;
   int nsb = h->decode_subbatches > 0 ? h->decode_subbatches : 1;  // measured on B200: 2 sub-batches gain 1.5 %, more lose (k_detect is latency-bound per image)
   if (const char* env = getenv("SPVO_DECODE_SUBBATCHES")) nsb = atoi(env) > 0 ? atoi(env) : nsb;  // tuning knob
   if (nsb > B) nsb = B;
-  if (nsb <= 1) return launch_decode_range(h, semi, desc, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+  if (nsb <= 1) return launch_decode_range(h, semi, desc, in_f16, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink);
   cudaError_t e;
   if (!h->aux_stream[0]) {
     for (int i = 0; i < 2; ++i) {
@@ -1080,7 +1135,7 @@ cudaError_t launch_decode(Handle* h, const float* semi, const float* desc, int B
   for (int sb = 0; sb < nsb && rc == cudaSuccess; ++sb) {
     const int b0 = (int)((long long)B * sb / nsb), b1 = (int)((long long)B * (sb + 1) / nsb);
     h->stream = h->aux_stream[sb & 1];
-    rc = launch_decode_range(h, semi, desc, b0, b1 - b0, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+    rc = launch_decode_range(h, semi, desc, in_f16, b0, b1 - b0, H, W, cfg, kpts, desc_out, n_out, scores, sink);
   }
   h->stream = main_st;
   for (int i = 0; i < 2; ++i) {

@@ -117,14 +117,17 @@ class Frontend:
     # ---- decode -------------------------------------------------------------------------------
     def decode(self, semi: np.ndarray, desc: Optional[np.ndarray], conf_thresh=0.015, dist_thresh=4,
                border_remove=4, max_keypoints=1000, want_scores=True):
-        """Host-buffer decode (spvo_decode).  semi [B,65,Hc,Wc], desc [B,256,Hc,Wc] numpy fp32."""
-        semi = np.ascontiguousarray(semi, np.float32)
+        """Host-buffer decode (spvo_decode / spvo_decode_f16).  semi [B,65,Hc,Wc], desc [B,256,Hc,Wc] numpy fp32, or
+        both float16 (an fp16 engine's outputs; results equal those of the widened fp32 tensors bit for bit)."""
+        f16 = np.asarray(semi).dtype == np.float16
+        dt = np.float16 if f16 else np.float32
+        semi = np.ascontiguousarray(semi, dt)
         B, Cc, Hc, Wc = semi.shape
         if Cc != 65:
             raise ValueError("semi must be [B,65,Hc,Wc]")
         K = int(max_keypoints)
         if desc is not None:
-            desc = np.ascontiguousarray(desc, np.float32)
+            desc = np.ascontiguousarray(desc, dt)
             if desc.shape != (B, 256, Hc, Wc):
                 raise ValueError("desc must be [B,256,Hc,Wc]")
         kp = np.zeros((B, K), KEYPOINT_DTYPE)
@@ -132,16 +135,18 @@ class Frontend:
         n = np.zeros(B, np.int32)
         sc = np.zeros((B, K), np.float32) if want_scores else None
         cfg = DecodeCfg(conf_thresh, dist_thresh, border_remove, K)
-        self._check(self._L.spvo_decode(self._h, _ptr(semi), _ptr(desc), B, Hc * 8, Wc * 8, C.byref(cfg), _ptr(kp),
-                                        _ptr(dout), _ptr(n), _ptr(sc)))
+        fn = self._L.spvo_decode_f16 if f16 else self._L.spvo_decode
+        self._check(fn(self._h, _ptr(semi), _ptr(desc), B, Hc * 8, Wc * 8, C.byref(cfg), _ptr(kp), _ptr(dout), _ptr(n),
+                       _ptr(sc)))
         return dict(kpts=kp, desc=dout, n=n, scores=sc)
 
     def decode_device(self, semi, desc, B, H, W, kpts_out, desc_out, n_out, scores_out=None, conf_thresh=0.015,
-                      dist_thresh=4, border_remove=4, max_keypoints=1000):
-        """Device-pointer decode (spvo_decode_device): torch CUDA tensors or raw pointers; async."""
+                      dist_thresh=4, border_remove=4, max_keypoints=1000, f16=False):
+        """Device-pointer decode (spvo_decode_device[_f16]): torch CUDA tensors or raw pointers; async."""
         cfg = DecodeCfg(conf_thresh, dist_thresh, border_remove, int(max_keypoints))
-        self._check(self._L.spvo_decode_device(self._h, _ptr(semi), _ptr(desc), B, H, W, C.byref(cfg),
-                                               _ptr(kpts_out), _ptr(desc_out), _ptr(n_out), _ptr(scores_out)))
+        fn = self._L.spvo_decode_device_f16 if f16 else self._L.spvo_decode_device
+        self._check(fn(self._h, _ptr(semi), _ptr(desc), B, H, W, C.byref(cfg), _ptr(kpts_out), _ptr(desc_out),
+                       _ptr(n_out), _ptr(scores_out)))
 
     # ---- match --------------------------------------------------------------------------------
     def match(self, q: np.ndarray, t: np.ndarray, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO):
@@ -189,24 +194,26 @@ class Frontend:
 
     def stereo_batch_device(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
                             max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
-                            stereo_threshold=2.0, min_disparity=0.25):
-        """spvo_stereo_batch_device.  `out` maps the spvo_stereo_out field names to CUDA tensors."""
+                            stereo_threshold=2.0, min_disparity=0.25, f16=False):
+        """spvo_stereo_batch_device[_f16].  `out` maps the spvo_stereo_out field names to CUDA tensors; f16=True:
+        semi / desc are float16 tensors (an fp16 engine's output bindings)."""
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
                                stereo_threshold, min_disparity)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
                               ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
-        self._check(self._L.spvo_stereo_batch_device(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg),
-                                                     C.byref(so)))
+        fn = self._L.spvo_stereo_batch_device_f16 if f16 else self._L.spvo_stereo_batch_device
+        self._check(fn(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg), C.byref(so)))
 
     def stereo_batch(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
                      max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
-                     stereo_threshold=2.0, min_disparity=0.25):
-        """spvo_stereo_batch (host pointers: numpy arrays or pinned CPU torch tensors); synchronous."""
+                     stereo_threshold=2.0, min_disparity=0.25, f16=False):
+        """spvo_stereo_batch[_f16] (host pointers: numpy arrays or pinned CPU torch tensors); synchronous."""
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
                                stereo_threshold, min_disparity)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
                               ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
-        self._check(self._L.spvo_stereo_batch(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg), C.byref(so)))
+        fn = self._L.spvo_stereo_batch_f16 if f16 else self._L.spvo_stereo_batch
+        self._check(fn(self._h, _ptr(semi), _ptr(desc), F, H, W, C.byref(cfg), C.byref(so)))
 
     @staticmethod
     def alloc_stereo_out(F, K, device="cuda", pinned=False, with_desc=True):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(spvo):
     for n in names:
         assert hasattr(L, n), f"{n} declared in spvo_frontend.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list and header disagree"
-    assert L.spvo_abi_version() == 2
+    assert L.spvo_abi_version() == 3
 
 
 def test_pod_layouts(spvo):
