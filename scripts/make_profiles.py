@@ -19,7 +19,7 @@ agg = {}
 for r in rows[hi + 1:]:
     if len(r) <= mv:
         continue
-    name = r[kn].split("(")[0].replace("spvo::", "")
+    name = r[kn].split("(")[0].replace("spvo::", "").replace("void ", "").split("<")[0]
     try:
         v = float(r[mv].replace(",", ""))
     except ValueError:
@@ -43,7 +43,7 @@ ix = {h: i for i, h in enumerate(hdr)}
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 o = {}
 for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0].replace("spvo::", "")
+    name = r[ix["Kernel Name"]].split("(")[0].replace("spvo::", "").replace("void ", "").split("<")[0]
     t = sum(float(r[ix[m]].replace(",", "")) * mult[units[ix[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     o.setdefault(f"{name}@F{F}", t)
 json.dump(o, open("profiles/ncu_traffic.json", "w"), indent=1)

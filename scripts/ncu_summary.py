@@ -21,7 +21,7 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
 print(f"# {rep}: one row per captured launch (ncu --set full --clock-control none); cold-cache, serialised")
 print("kernel".ljust(22) + "".join(n.rjust(16) for _, n in want))
 for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0].replace("spvo::", "")
+    name = r[ix["Kernel Name"]].split("(")[0].replace("spvo::", "").replace("void ", "").split("<")[0]
     out = name[:21].ljust(22)
     for m, _ in want:
         if m in ix:
