@@ -144,3 +144,23 @@ def test_match_tensor_max_size_8192(spvo, oracle):
     assert len(gm) == len(om) > 7000 and (gm["queryIdx"] == om["queryIdx"]).all() and (gm["trainIdx"] == om["trainIdx"]).all()
     assert (gm["distance"].view(np.uint32) == om["distance"].view(np.uint32)).all() and (gmap == omap).all()
     fe.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("scale", [1e-3, 37.0, 1e4])
+def test_match_tensor_arbitrary_descriptor_scale(spvo, oracle, mode, scale):
+    """Generic CV_32F descriptors are not unit-norm: the bf16 bound, the key offset and the key quantisation all
+    scale with the operands' largest norms.  Mixed row norms (x0.25 .. x4), a few all-zero rows, tensor path."""
+    rng = np.random.default_rng(int(scale * 10) % 1000 + mode)
+    N, M = 300, 520
+    base = unit_rows(M, seed=77)
+    q = (base[:N] + 0.05 * rng.standard_normal((N, 256)).astype(np.float32)).astype(np.float32)
+    t = base[rng.permutation(M)].copy()
+    q *= (np.float32(scale) * rng.choice(np.array([0.25, 1.0, 4.0], np.float32), size=(N, 1))).astype(np.float32)
+    t *= (np.float32(scale) * rng.choice(np.array([0.25, 1.0, 4.0], np.float32), size=(M, 1))).astype(np.float32)
+    q[5] = 0.0
+    t[9] = 0.0
+    t[11] = 0.0
+    fe = spvo.Frontend(0, 1, 64, 64, 16)
+    _check(fe, oracle, q, t, mode, 2)
+    fe.close()
