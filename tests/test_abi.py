@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol(spvo):
     for n in names:
         assert hasattr(L, n), f"{n} declared in spvo_frontend.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list and header disagree"
-    assert L.spvo_abi_version() == 3
+    hdr = open(os.path.join(ROOT, "include", "spvo_frontend.h")).read()
+    assert L.spvo_abi_version() == int(re.search(r"#define\s+SPVO_ABI_VERSION\s+(\d+)", hdr).group(1)) == 3
 
 
 def test_pod_layouts(spvo):
@@ -62,3 +63,9 @@ def test_product_never_imports_oracle():
                     "oracle and", "").replace("the CPU oracle", "").replace("passes the oracle", "").lower() or \
                     "import oracle" not in txt and "from oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt and "libspvo_oracle" not in txt
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """The driver's "does it build" check: compile everything (nvcc cross-compiles without a GPU) and load the ABI."""
+    import __graft_entry__ as g
+    g.build()
