@@ -67,3 +67,27 @@ def test_preprocess_invalid_arguments_and_mirror(spvo, oracle):
     oi, ors, oP = oracle.preprocess(img, 120, 392, P)
     m.preprocessImage(img, P, 1)
     assert (m.input_data_[1] == oi).all() and (m.images_dq[-1] == ors).all() and (P == oP).all()
+
+
+def test_preprocess_random_geometries(spvo, oracle):
+    """40 random (source size, network input size) pairs incl. odd widths (scalar store tail) and heavy up / down
+    scaling; one handle, so the coefficient-table cache is exercised across changing geometries."""
+    rng = np.random.default_rng(99)
+    fe = spvo.Frontend(0, 2, 64, 64, 16)
+    done = 0
+    for _ in range(60):
+        rows, cols = int(rng.integers(9, 400)), int(rng.integers(9, 600))
+        H, W = int(rng.integers(8, 300)), int(rng.integers(8, 400))
+        try:
+            oracle.crop_geometry(rows, cols, H, W)
+        except ValueError:
+            continue
+        imgs = rng.integers(0, 256, (2, rows, cols), dtype=np.uint8)
+        inp, rs, _ = fe.preprocess(imgs, H, W)
+        for b in range(2):
+            oi, ors, _ = oracle.preprocess(imgs[b], H, W)
+            assert (rs[b] == ors).all(), ((rows, cols), (H, W), int((rs[b] != ors).sum()))
+            assert (inp[b].view(np.uint32) == oi.view(np.uint32)).all()
+        done += 1
+    assert done >= 40
+    fe.close()

@@ -78,3 +78,20 @@ def test_projection_matrix_patch(oracle):
     exp[1, 2] -= np.float32(144)
     exp[:2] *= np.float32(640) / np.float32(640)
     assert (Pp.view(np.uint32) == exp.view(np.uint32)).all()
+
+
+def test_live_cv2_random_geometries(oracle):
+    """80 random (source size, network input size) pairs, up- and down-scaling by up to ~6x in either direction."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2024)
+    for _ in range(80):
+        rows, cols = int(rng.integers(9, 400)), int(rng.integers(9, 600))
+        H, W = int(rng.integers(8, 300)), int(rng.integers(8, 400))
+        try:
+            cr, cc, ro, co = oracle.crop_geometry(rows, cols, H, W)
+        except ValueError:
+            continue  # empty crop (extreme aspect ratios)
+        img = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+        ref = cv2.resize(img[ro:ro + cr, co:co + cc], (W, H), interpolation=cv2.INTER_LINEAR)
+        rs = oracle.preprocess(img, H, W)[1]
+        assert (rs == ref).all(), ((rows, cols), (H, W), (cr, cc, ro, co), int((rs != ref).sum()))
