@@ -85,3 +85,22 @@ def test_stereo_batch_f16_matches_the_widened_fp32_run(spvo):
             _same_valid(S, oa, o, F, K)
     for f in (fa, fb, fc):
         f.close()
+
+
+def test_stereo_batch_f16_host_chunked_path(spvo):
+    """F >= 16: the host form streams the batch as 4 chunks; with fp16 inputs every chunk offset is in 2-byte
+    elements.  Must equal the fp32 host call on the widened tensors."""
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, F = 128, 320, 200, 18
+    semi, desc = synth.make_stream(F, H, W, seed=31, device="cpu")
+    s16, d16 = semi.numpy().astype(np.float16), desc.numpy().astype(np.float16)
+    fa, fb = S.Frontend(0, 2 * F, H, W, K), S.Frontend(0, 2 * F, H, W, K)
+    oa = {k: v.numpy() for k, v in fa.alloc_stereo_out(F, K, device="cpu").items()}
+    ob = {k: v.numpy() for k, v in fb.alloc_stereo_out(F, K, device="cpu").items()}
+    fa.stereo_batch(s16.astype(np.float32), d16.astype(np.float32), F, H, W, oa, max_keypoints=K)
+    fb.stereo_batch(s16, d16, F, H, W, ob, max_keypoints=K, f16=True)
+    assert oa["n_matches"].sum() > 1000
+    _same_valid(S, oa, ob, F, K)
+    fa.close()
+    fb.close()
