@@ -48,6 +48,11 @@ def lib():
         L.spvo_oracle_l2dist.argtypes = [vp, vp, C.c_int]
         L.spvo_oracle_heatmap.restype = C.c_int
         L.spvo_oracle_heatmap.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.spvo_oracle_heatmap_variant.restype = C.c_int
+        L.spvo_oracle_heatmap_variant.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+        L.spvo_oracle_detect.restype = C.c_int
+        L.spvo_oracle_detect.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         vp, vp, vp]
         L.spvo_oracle_decode.restype = C.c_int
         L.spvo_oracle_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                          C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -94,6 +99,31 @@ def heatmap(semi, num_threads: int = 1) -> np.ndarray:
     rc = lib().spvo_oracle_heatmap(_p(semi), B, Hc * 8, Wc * 8, _p(heat), num_threads)
     assert rc == 0
     return heat
+
+
+VAR_LIBM_EXP, VAR_CEPHES_NOFMA, VAR_PAIRWISE_SUM = 1, 2, 4
+
+
+def heatmap_variant(semi, variant: int, num_threads: int = 1) -> np.ndarray:
+    """Sensitivity study only: the heatmap with another plausible exp / channel-sum build (variant 0 = the spec)."""
+    semi = _f32(semi)
+    B, Cc, Hc, Wc = semi.shape
+    heat = np.empty((B, Hc * 8, Wc * 8), np.float32)
+    assert lib().spvo_oracle_heatmap_variant(_p(semi), B, Hc * 8, Wc * 8, _p(heat), num_threads, int(variant)) == 0
+    return heat
+
+
+def detect(heat, conf_thresh=0.015, dist_thresh=4, border_remove=4, max_keypoints=1000, faithful_sort=False):
+    """Rows D3-D5 (threshold, sort, greedy NMS, border, top-K) on a given heatmap [B,H,W]."""
+    heat = _f32(heat)
+    B, H, W = heat.shape
+    K = int(max_keypoints)
+    kp = np.zeros((B, K), KEYPOINT_DTYPE)
+    sc = np.zeros((B, K), np.float32)
+    n = np.zeros(B, np.int32)
+    assert lib().spvo_oracle_detect(_p(heat), B, H, W, float(conf_thresh), int(dist_thresh), int(border_remove), K,
+                                    int(bool(faithful_sort)), _p(kp), _p(sc), _p(n)) == 0
+    return dict(kpts=kp, scores=sc, n=n)
 
 
 def decode(semi, desc, conf_thresh=0.015, dist_thresh=4, border_remove=4, max_keypoints=1000,

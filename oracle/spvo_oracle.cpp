@@ -97,6 +97,53 @@ inline float oracle_exp(float x0) {
   return std::fmax(y * scale, x0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SENSITIVITY VARIANTS (tests/test_oracle_sensitivity.py).  The decode oracle is "parity unpinned": the
+// reference's exp / reduction bits belong to an Eigen build that cannot be reproduced here.  These
+// variants restate the other plausible builds so that the tests can MEASURE how far a real build can move
+// the result:
+//   kVarLibmExp      exp = glibc expf (correctly rounded in practice; the upper bound on accuracy)
+//   kVarCephesNoFma  Eigen 3.3 pexp as compiled WITHOUT FMA (SSE2 build): fx = x*LOG2E + 0.5 (two ops), floor,
+//                    r = (x - fx*C1) - fx*C2 with Cephes' split ln2, Horner with separate multiply / add
+//   kVarPairwiseSum  channel sum as a balanced tree (a vectorised / tree reduction) instead of c = 0..64 in order
+// ---------------------------------------------------------------------------------------------
+enum { kVarLibmExp = 1, kVarCephesNoFma = 2, kVarPairwiseSum = 4 };
+
+inline float cephes_exp_nofma(float x0) {
+  float x = std::fmin(std::fmax(x0, -88.3762626647949f), 88.3762626647950f);
+  float fx = x * 1.44269504088896341f;
+  fx = fx + 0.5f;
+  fx = std::floor(fx);
+  float tmp = fx * 0.693359375f;
+  float z = fx * -2.12194440e-4f;
+  x = x - tmp;
+  x = x - z;
+  z = x * x;
+  float y = 1.9875691500E-4f;
+  y = y * x; y = y + 1.3981999507E-3f;
+  y = y * x; y = y + 8.3334519073E-3f;
+  y = y * x; y = y + 4.1665795894E-2f;
+  y = y * x; y = y + 1.6666665459E-1f;
+  y = y * x; y = y + 5.0000001201E-1f;
+  y = y * z; y = y + x;
+  y = y + 1.0f;
+  int e = (int)fx + 127;
+  float scale = u2f((uint32_t)e << 23);
+  return std::fmax(y * scale, x0);
+}
+
+inline float variant_exp(float x, int variant) {
+  if (variant & kVarLibmExp) return std::exp(x);
+  if (variant & kVarCephesNoFma) return cephes_exp_nofma(x);
+  return oracle_exp(x);
+}
+
+inline float tree_sum(const float* v, int n) {  // balanced binary tree, left half first
+  if (n == 1) return v[0];
+  const int h = (n + 1) / 2;
+  return tree_sum(v, h) + tree_sum(v + h, n - h);
+}
+
 template <class F>
 void run_parallel(int n, int num_threads, F&& fn) {
   if (num_threads <= 1 || n <= 1) {
@@ -121,7 +168,7 @@ void run_parallel(int n, int num_threads, F&& fn) {
 //   p_c  = e_c / (s + 1e-5f)   true division          (:280-284)
 //   heat[8*hc + i, 8*wc + j] = p_{8*i + j}[hc, wc]    (:289-326)
 // ---------------------------------------------------------------------------------------------
-void softmax_heatmap(const float* semi, int Hc, int Wc, float* heat, int num_threads) {
+void softmax_heatmap(const float* semi, int Hc, int Wc, float* heat, int num_threads, int variant = 0) {
   const int W = Wc * 8;
   const int cells = Hc * Wc;
   run_parallel(Hc, num_threads, [&](int r_lo, int r_hi) {
@@ -130,9 +177,15 @@ void softmax_heatmap(const float* semi, int Hc, int Wc, float* heat, int num_thr
       for (int wc = 0; wc < Wc; ++wc) {
         const float* src = semi + hc * Wc + wc;
         float s = 0.0f;
-        for (int c = 0; c < 65; ++c) {
-          e[c] = oracle_exp(src[(size_t)c * cells]);
-          s = s + e[c];
+        if (variant == 0) {
+          for (int c = 0; c < 65; ++c) {
+            e[c] = oracle_exp(src[(size_t)c * cells]);
+            s = s + e[c];
+          }
+        } else {  // sensitivity variants only (never the specification)
+          for (int c = 0; c < 65; ++c) e[c] = variant_exp(src[(size_t)c * cells], variant);
+          if (variant & kVarPairwiseSum) s = tree_sum(e, 65);
+          else for (int c = 0; c < 65; ++c) s = s + e[c];
         }
         const float denom = s + 0.00001f;
         for (int i = 0; i < 8; ++i) {
@@ -301,6 +354,31 @@ int spvo_oracle_heatmap(const float* semi, int B, int H, int W, float* heat, int
   const int Hc = H / 8, Wc = W / 8;
   for (int b = 0; b < B; ++b)
     softmax_heatmap(semi + (size_t)b * 65 * Hc * Wc, Hc, Wc, heat + (size_t)b * H * W, num_threads);
+  return 0;
+}
+
+// Sensitivity study only: heatmap with a VARIANT exp / channel-sum (see kVar* above; variant 0 = the specification).
+int spvo_oracle_heatmap_variant(const float* semi, int B, int H, int W, float* heat, int num_threads, int variant) {
+  if (!semi || !heat || B < 0 || H <= 0 || W <= 0 || H % 8 || W % 8) return 1;
+  const int Hc = H / 8, Wc = W / 8;
+  for (int b = 0; b < B; ++b)
+    softmax_heatmap(semi + (size_t)b * 65 * Hc * Wc, Hc, Wc, heat + (size_t)b * H * W, num_threads, variant);
+  return 0;
+}
+
+// Rows D3-D5 on a GIVEN heatmap (feature_detection_neural_network.cpp:188-262): used by the sensitivity study to run
+// the reference's walk on variant heatmaps.  kpts_out [B,K], scores_out [B,K] (optional), n_out [B].
+int spvo_oracle_detect(const float* heat, int B, int H, int W, float conf_thresh, int dist_thresh, int border_remove,
+                       int max_keypoints, int faithful_sort, spvo_keypoint* kpts_out, float* scores_out, int* n_out) {
+  if (!heat || !kpts_out || !n_out || B < 0 || H <= 0 || W <= 0 || max_keypoints < 0) return 1;
+  for (int b = 0; b < B; ++b) {
+    spvo_keypoint* kp = kpts_out + (size_t)b * max_keypoints;
+    const int n = detect_one(heat + (size_t)b * H * W, H, W, conf_thresh, dist_thresh, border_remove, max_keypoints,
+                             faithful_sort, kp, scores_out ? scores_out + (size_t)b * max_keypoints : nullptr, nullptr,
+                             nullptr);
+    for (int i = n; i < max_keypoints; ++i) kp[i] = spvo_keypoint{0, 0, 0, 0, 0, 0, 0};
+    n_out[b] = n;
+  }
   return 0;
 }
 

@@ -142,6 +142,7 @@ int spvo_destroy(spvo_handle hh) {
     if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
   }
   if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+  if (h->pp_done) cudaEventDestroy(h->pp_done);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 5; ++i)
     if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
@@ -521,8 +522,9 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
   const int carry_slot = h->max_batch;
   TcSink sink;
   if (tensor) CK(tc_prepare_slots(h, h->max_batch + 1, h->max_k, 2 * h->max_batch, &sink));
+  bool sink_filled = false;  // false when decode used the gather form (planes larger than shared memory)
   CK(launch_decode(h, semi, desc, in_f16, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr,
-                   tensor ? &sink : nullptr));
+                   tensor ? &sink : nullptr, &sink_filled));
   if (2 * F > h->probs_cap) {
     cudaFree(h->probs);
     h->probs = nullptr;
@@ -531,10 +533,12 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
     h->probs_cap = 2 * F;
   }
   CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot));
-  if (tensor && h->has_prev && !h->carry_tc_valid)
+  const bool ready = tensor && sink_filled;
+  if (ready && h->has_prev && !h->carry_tc_valid)
     // the previous batch ran on the exact matcher: convert the carried fp32 descriptors into the carry slot
     CK(tc_prep_problem_operands(h, h->probs + F));
-  rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K, tensor);
+  // !ready: the matcher converts every operand itself (k_tc_prep, bf16) -- decode did not fill the slots
+  rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K, ready);
   if (rc) return rc;
   if (keep)
     CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
@@ -549,13 +553,13 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
   cl.seg[cl.n++] = {desc_out + last * K * 256, h->carry_desc, (size_t)K * 256 * sizeof(float)};
   cl.seg[cl.n++] = {kpts + last * K, h->carry_kpts, (size_t)K * sizeof(spvo_keypoint)};
   cl.seg[cl.n++] = {n_kpts + last, h->carry_n, sizeof(int)};
-  if (tensor) cl.n += tc_copy_slot_segments(h, carry_slot, (int)last, cl.seg + cl.n);
+  if (ready) cl.n += tc_copy_slot_segments(h, carry_slot, (int)last, cl.seg + cl.n);
   {
     LaunchScope ls(h, KID_CARRY);
     k_carry_copy<<<dim3(64, cl.n), 256, 0, st>>>(cl);
   }
   CK(cudaGetLastError());
-  h->carry_tc_valid = tensor;
+  h->carry_tc_valid = ready;
   h->has_prev = true;
   return SPVO_OK;
 }

@@ -53,7 +53,7 @@ struct TcSink {
 // semi / desc: fp32 (in_f16 = 0) or fp16 (in_f16 = 1) device tensors
 cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                          float* scores, const TcSink* sink = nullptr);
+                          float* scores, const TcSink* sink = nullptr, bool* sink_filled = nullptr);
 // ---- match.cu ----
 cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                                const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
@@ -112,6 +112,7 @@ struct Handle {
   size_t pp_tab_cap = 0;
   int pp_key[4] = {-1, -1, -1, -1};
   cudaStream_t pp_stream = nullptr;
+  cudaEvent_t pp_done = nullptr;   // recorded after the last k_preprocess (orders a table rebuild on another stream)
   unsigned long long* counters = nullptr;  // [8] device counters (slow path images, fallback rows, ...)
   // staging for the host-pointer entry points
   float* st_semi = nullptr;

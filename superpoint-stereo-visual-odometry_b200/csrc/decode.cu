@@ -120,6 +120,9 @@ struct DetectParams {
 };
 
 constexpr int kDetectThreads = 512;
+// A heat value is a candidate iff it compares '>' conf as a float (NN:203): NaN (non-finite logits) never is, although
+// its bit pattern is above every finite one -- the raw-bit predicates exclude everything from +inf upwards.
+constexpr uint32_t kInfBits = 0x7F800000u;
 typedef unsigned long long u64;
 
 struct Scan {  // running (x, y) of a thread's current float4 while striding over the heatmap
@@ -178,7 +181,7 @@ __device__ int collect_keys(const float* heat, int H, int W, uint32_t conf_bits,
   const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
   const int lane = threadIdx.x & 31;
   scan_heat(
-      heat, H, W, [&](uint32_t b) { return b > conf_bits && b >= lo_b && b <= hi_b; },
+      heat, H, W, [&](uint32_t b) { return b > conf_bits && b >= lo_b && b <= hi_b && b < kInfBits; },
       [&](bool s, uint32_t b, int x, int y) {
         u64 key = make_key(b, x, y, H);
         s = s && key >= lo && key < hi;
@@ -295,7 +298,7 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const uint2* _
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const uint32_t bts = fbits(pv[e]);
-        bool s = ok[u] && bts > conf_bits && bts >= lo_b;
+        bool s = ok[u] && bts > conf_bits && bts >= lo_b && bts < kInfBits;
         if (s && bts == lo_b) s = make_key(bts, cx[u] + e, cy[u], H) >= lo;  // boundary score: full key comparison
         mask |= (s ? 1u : 0u) << (4 * u + e);
       }
@@ -344,7 +347,7 @@ __device__ u64 radix_select(const float* heat, int H, int W, uint32_t conf_bits,
     __syncthreads();
     const u64 prefix = *s_prefix;
     scan_heat(
-        heat, H, W, [&](uint32_t b) { return b > conf_bits && b <= hi_b; },
+        heat, H, W, [&](uint32_t b) { return b > conf_bits && b <= hi_b && b < kInfBits; },
         [&](bool s, uint32_t b, int x, int y) {
           u64 key = make_key(b, x, y, H);
           s = s && key < hi && (pass == 0 || (key >> (shift + 8)) == prefix);
@@ -1003,7 +1006,7 @@ static size_t detect_smem_bytes(int H, int W, int K, int cap) {
 static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void* desc_v, int in_f16, int b0, int B,
                                        int H, int W,
                                        const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                                       float* scores, const TcSink* sink) {
+                                       float* scores, const TcSink* sink, bool* sink_filled) {
   cudaStream_t st = h->stream;
   const int Hc = H / 8, Wc = W / 8, cells = Hc * Wc, K = cfg.max_keypoints;
   cudaError_t e;
@@ -1037,6 +1040,9 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
     const int plane_pitch = (cells + per16 + per16 - 1) & ~(per16 - 1);
     const size_t smem_planes = (size_t)kCP * plane_pitch * esz;
     const bool streaming = desc && desc_out && h->desc_tmp && h->kp_par && smem_planes <= 200 * 1024;
+    // only the streaming form writes the tensor matcher's operands; the gather form (planes larger than shared
+    // memory) leaves the sink untouched and the caller must run k_tc_prep instead
+    if (sink_filled) *sink_filled = streaming && sink && sink->xb;
     int4* kp_par = streaming ? h->kp_par + (size_t)b0 * K : nullptr;
     const int Kp = (K + 3) & ~3;  // scratch pitch: 16-byte loads in k_desc_normalize
     float* tmp = streaming ? h->desc_tmp + (size_t)b0 * 256 * Kp : nullptr;
@@ -1113,12 +1119,13 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
 // latency-bound per-image k_detect of one sub-batch overlaps the bandwidth-bound kernels of the other.
 cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
-                          float* scores, const TcSink* sink) {
+                          float* scores, const TcSink* sink, bool* sink_filled) {
+  if (sink_filled) *sink_filled = false;
   if (B == 0) return cudaSuccess;
   int nsb = h->decode_subbatches > 0 ? h->decode_subbatches : 1;  // measured on B200: 2 sub-batches gain 1.5 %, more lose (k_detect is latency-bound per image)
   if (const char* env = getenv("SPVO_DECODE_SUBBATCHES")) nsb = atoi(env) > 0 ? atoi(env) : nsb;  // tuning knob
   if (nsb > B) nsb = B;
-  if (nsb <= 1) return launch_decode_range(h, semi, desc, in_f16, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+  if (nsb <= 1) return launch_decode_range(h, semi, desc, in_f16, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink, sink_filled);
   cudaError_t e;
   if (!h->aux_stream[0]) {
     for (int i = 0; i < 2; ++i) {
@@ -1135,7 +1142,7 @@ cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_
   for (int sb = 0; sb < nsb && rc == cudaSuccess; ++sb) {
     const int b0 = (int)((long long)B * sb / nsb), b1 = (int)((long long)B * (sb + 1) / nsb);
     h->stream = h->aux_stream[sb & 1];
-    rc = launch_decode_range(h, semi, desc, in_f16, b0, b1 - b0, H, W, cfg, kpts, desc_out, n_out, scores, sink);
+    rc = launch_decode_range(h, semi, desc, in_f16, b0, b1 - b0, H, W, cfg, kpts, desc_out, n_out, scores, sink, sink_filled);
   }
   h->stream = main_st;
   for (int i = 0; i < 2; ++i) {

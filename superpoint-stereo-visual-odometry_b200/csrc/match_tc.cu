@@ -1017,10 +1017,14 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       if (!w || w->top_rows < (size_t)ndir * w->slot_cap) return cudaErrorInvalidValue;
       cap = w->slot_cap;
     } else {
-      if ((e = tc_get(h, &w, (size_t)2 * P, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
+      // operand slots are the problems' a_op / b_op: 2p, 2p+1 for the generic entry points, image indices (and the
+      // carry slot max_batch) for a stereo batch whose decode could not fill them
+      const size_t ops = (size_t)(2 * P > h->max_batch + 1 ? 2 * P : h->max_batch + 1);
+      if ((e = tc_get(h, &w, ops, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
       w->slot_cap = cap;
       w->fp16 = false;  // arbitrary CV_32F descriptors: bf16 keeps the fp32 exponent range
-      if ((e = cudaMemsetAsync(w->opmax, 0, (size_t)2 * P * sizeof(unsigned), st)) != cudaSuccess) return e;
+      h->carry_tc_valid = false;  // the slots (and possibly the buffers) of a previous stereo batch are overwritten
+      if ((e = cudaMemsetAsync(w->opmax, 0, ops * sizeof(unsigned), st)) != cudaSuccess) return e;
       LaunchScope ls(h, KID_TC_PREP);
       k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap, 0);
     }

@@ -133,7 +133,9 @@ cudaError_t launch_preprocess(Handle* h, const uint8_t* imgs, int B, int rows, i
   const bool area2x = (W * 2 == cc && H * 2 == cr);
   if (!area2x && (h->pp_key[0] != cr || h->pp_key[1] != cc || h->pp_key[2] != H || h->pp_key[3] != W ||
                   h->pp_stream != h->stream)) {  // (a different stream has no ordering with the table kernel)
-    // coefficient tables for this geometry (kept until the geometry changes: one camera, one network input size)
+    // coefficient tables for this geometry (kept until the geometry changes: one camera, one network input size).
+    // A k_preprocess launched earlier (possibly on another stream) may still read the old table: order behind it.
+    if (h->pp_done && (e = cudaStreamWaitEvent(h->stream, h->pp_done, 0)) != cudaSuccess) return e;
     if (h->pp_tab_cap < (size_t)(W + H)) {
       cudaFree(h->pp_tab);
       h->pp_tab = nullptr;
@@ -157,9 +159,13 @@ cudaError_t launch_preprocess(Handle* h, const uint8_t* imgs, int B, int rows, i
   p.xtab = h->pp_tab;
   p.ytab = h->pp_tab ? h->pp_tab + W : nullptr;
   p.out_f = out_f; p.out_u8 = out_u8;
-  LaunchScope ls(h, KID_PREPROCESS);
-  k_preprocess<<<dim3((W + 127) / 128, (H + 7) / 8, B), 256, 0, h->stream>>>(p);
-  return cudaGetLastError();
+  {
+    LaunchScope ls(h, KID_PREPROCESS);
+    k_preprocess<<<dim3((W + 127) / 128, (H + 7) / 8, B), 256, 0, h->stream>>>(p);
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (!h->pp_done && (e = cudaEventCreateWithFlags(&h->pp_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+  return cudaEventRecord(h->pp_done, h->stream);
 }
 
 }  // namespace spvo

@@ -280,6 +280,7 @@ class SuperPointFeatureFrontEnd:
         self.maps_of_indices = [np.zeros(0, np.int32) for _ in range(MATCH_TYPE_NUM)]       # hpp:161
 
     def clearLagecyData(self):  # BASE:35-66 (sic)
+        self.images_dq.clear()       # BASE:36
         self.keypoints_dq.clear()
         self.descriptors_dq.clear()
         self.cv_DMatches_list = [np.zeros(0, DMATCH_DTYPE) for _ in range(MATCH_TYPE_NUM)]
@@ -303,6 +304,8 @@ class SuperPointFeatureFrontEnd:
         while len(self.keypoints_dq) > 4:                        # NN:494-498
             self.keypoints_dq.popleft()
             self.descriptors_dq.popleft()
+        while len(self.images_dq) > 4:                           # NN:494-498 trims all three deques together
+            self.images_dq.popleft()
 
     def matchDescriptors(self, match_type: int):  # BASE:434-500
         p0, p1 = match_type_to_positions[match_type]
