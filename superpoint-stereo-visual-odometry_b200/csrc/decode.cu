@@ -946,11 +946,11 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
   float smax = 0.f;
   for (int kk = w; kk < 32; kk += 8) {
     const int k = k0 + kk;
-    if (xb && k < sink.cap && k >= n) {  // padded rows of the matcher slot: zero row, norm = +inf
+    if (xb && k < sink.cap && k >= n) {  // padded rows of the matcher slot: zero row, norm = NaN (match_tc.cu: pad_norm)
       const size_t row = (size_t)b * sink.cap + k;
 #pragma unroll
       for (int i = 0; i < 8; ++i) xb[row * 256 + lane + 32 * i] = 0;
-      if (lane == 0) sink.nrm[row] = INFINITY;
+      if (lane == 0) sink.nrm[row] = __uint_as_float(0x7FFFFFFFu);
     }
     if (k >= K) continue;
     float* o = out + ((size_t)b * K + k) * 256;

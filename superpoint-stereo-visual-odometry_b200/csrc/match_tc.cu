@@ -8,17 +8,21 @@
 //   k_tc_prep       fp32 descriptors -> 16-bit rows (bf16) + fp32 squared norms in a row-padded workspace.
 //                   Not used by the stereo pipeline: k_desc_normalize (decode.cu) writes fp16 operands of
 //                   its unit-norm descriptors straight into the workspace.
-//   k_tc_gemm       persistent, one CTA per SM over (directed problem, 128-row block) items:
+//   k_tc_gemm       persistent, one CTA per SM over (problem, 128-row block) items: ONE Gram matrix per match,
 //                   S = A . B^T with tcgen05.mma (cta_group::1, M = 128, N = 256, K = 16, 16-bit -> fp32 in
 //                   TMEM), A block resident per item, B streamed by TMA (128 B swizzle) as a ring of 32 KB
-//                   k-blocks, two 256-column accumulators in TMEM; 8 epilogue warps read TMEM with tcgen05.ld
-//                   and keep, per row, the 3 smallest g_ij = |b_j|^2 - 2 S_ij with their column indices IN
-//                   REGISTERS as packed keys (the distance matrix never exists in memory)
-//   k_tc_triage     one thread per row: rows whose 2nd shortlist entry is outside the proved error bound
-//                   are decided with no further arithmetic; the rest are queued
+//                   k-blocks, two 256-column accumulators in TMEM; 8 epilogue warps read TMEM with
+//                   tcgen05.ld.16x256b and reduce every tile in BOTH directions IN REGISTERS: per row the two
+//                   smallest g_ij = |b_j|^2 - 2 S_ij of each thread's columns, per column the two smallest
+//                   h_ij = |a_i|^2 - 2 S_ij over the block's rows (cross-check), as packed 32-bit keys, each list
+//                   with a proved lower bound on everything it does not name (the distance matrix never exists
+//                   in memory, and the reverse direction costs no second GEMM)
+//   k_tc_triage     one thread per row / per train column: merges the sub-lists; entries whose runner-up (listed
+//                   or bounded) is outside the proved error bound are decided with no further arithmetic; the
+//                   rest are queued with a normalised shortlist
 //   k_tc_rerank     queued rows: every shortlisted column within the bound gets its distance recomputed
 //                   in OpenCV's fp32 operation order (bit-exact DMatch.distance, first-index ties); rows
-//                   whose whole shortlist is inside the bound go to the fallback worklist
+//                   whose unlisted columns are not provably outside the bound go to the fallback worklist
 //   k_tc_fallback   fp32 dot products of the queued rows against every column (8 rows per pass), then
 //                   exact distances for the columns within 2*eps32; if even that could be incomplete,
 //                   an exact scan of the whole row
@@ -32,8 +36,9 @@
 // A column whose approx d^2 exceeds the row minimum by more than 2*eps (plus the key truncation) cannot be
 // the exact minimum (nor tie with it).
 //
-// Cross-check needs the reverse nearest neighbour as well: it is a second directed problem
-// (B against A) in the same launch; D(a,b) is bitwise symmetric in OpenCV's arithmetic.
+// Cross-check needs the reverse nearest neighbour as well (BASE:462-463): it comes from the column direction of the
+// same accumulator tiles; D(a,b) is bitwise symmetric in OpenCV's arithmetic.  Downstream (triage, rerank, fallback)
+// the train -> query direction is handled as a second "directed problem" dp = P + p with the operand roles swapped.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -54,7 +59,6 @@ constexpr int kBSlotBytes = kBN * kKB * 2; // 32 KB per B k-block (256 columns x
 constexpr int kBSlots = 4;                // B k-blocks in flight (ring) = one whole tile ahead
 constexpr int kAccStages = 2;             // accumulator stages in TMEM
 constexpr int kTmemCols = kAccStages * kBN;  // 512: all of TMEM (one CTA per SM)
-constexpr int kLists = 2;                 // shortlists per row (one per 128-column half of a tile), merged by triage / rerank
 constexpr int kTop = 3;
 constexpr int kEpiWarps = 8;              // one per (TMEM lane quadrant, 128-column half of the tile)
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
@@ -63,15 +67,13 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + T
 //   fp16 operands (|x| <= 1, unit-norm rows): 2*(2^-10 + 2^-22 + 2^-14) -> 0.0022; fp16 subnormals (|x| < 2^-14) add
 //   <= 2*256*2^-25 per unit of max|b_k| -> covered by kEpsAbs.
 constexpr float kEpsRelBf16 = 0.0085f, kEpsRelFp16 = 0.0022f, kEpsAbs = 1e-5f;
-// packed key = (bits(g + off) & ~mask) | column, mask = 2^idx_bits - 1 with 2^idx_bits >= rows per slot;
-// truncating idx_bits mantissa bits loses < 2^(idx_bits-23) of the (positive) value
-constexpr int kMaxIdxBits = 13;
-
-// Offset that makes every g_ij + off positive, so fp32 bit patterns order like the values:
-// g = |b|^2 - 2 a.b >= -2|a||b| >= -2 sqrt(amax2 * bmax2).
-__device__ __forceinline__ float key_offset(float amax2, float bmax2) {
-  return 2.0f * sqrtf(amax2 * bmax2) * 1.01f + 1e-30f;  // 1.01 > (1 + 2^-9)^2: bf16 rounding can lengthen both vectors
-}
+// Key values live in [2, 8) after an affine map (tc_scale); their fp32 arithmetic (two fused multiply-adds, the
+// affine map and its inverse) is off by < 1e-6 per value in those units, and the row records keep 20 of the 24 value
+// bits (< 1.6e-5): kKeySlack covers a comparison of two.
+constexpr float kKeySlack = 4e-5f;
+// norm of a padded row / column: NaN, so that every key built from it is the canonical NaN 0x7FFFFFFF -> the largest
+// 24-bit key value (kNone24) -- padded entries never enter a shortlist
+__device__ __forceinline__ float pad_norm() { return __uint_as_float(0x7FFFFFFFu); }
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -98,6 +100,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// For the one-lane producer / MMA-issuer warps: back off between polls so that their spinning does not take issue
+// slots from the two epilogue warps that share their scheduler (ncu: 17 % of the kernel's issued instructions were
+// SYNCS / BRA / YIELD of these loops).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -153,7 +172,7 @@ __host__ __device__ constexpr uint32_t make_idesc(bool fp16) {
 
 // ------------------------------------------------------------------------------------------------
 // k_tc_prep: operand o = 2p (query of problem p) or 2p+1 (train).  One warp per workspace row.
-// Rows >= n are zero with norm = +inf, so padded columns never enter a shortlist.
+// Rows >= n are zero with norm = NaN (pad_norm), so padded rows / columns never enter a shortlist.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb, float* __restrict__ nrm,
@@ -201,7 +220,7 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     reinterpret_cast<uint4*>(xb + row * kDim)[lane] = packed;
-    if (lane == 0) nrm[row] = r < n ? s : INFINITY;
+    if (lane == 0) nrm[row] = r < n ? s : pad_norm();
     if (r < n) smax = fmaxf(smax, s);
   }
   if (lane == 0 && smax > 0.f) atomicMax(&opmax[slot], __float_as_uint(smax));
@@ -210,16 +229,37 @@ k_tc_prep(const MatchProblem* __restrict__ probs, __nv_bfloat16* __restrict__ xb
 // ------------------------------------------------------------------------------------------------
 // k_tc_gemm
 //
+// ONE Gram matrix per match.  S = A . B^T is computed once per (problem, 128-row block); the epilogue reduces
+// every accumulator tile in BOTH directions:
+//   rows    (query i -> nearest train j):  g_ij = |b_j|^2 - 2 S_ij   (+ constant in i)
+//   columns (train j -> nearest query i):  h_ij = |a_i|^2 - 2 S_ij   (+ constant in j)   [cross-check only]
+// so cv::BFMatcher's crossCheck (BASE:462-463: the reverse nearest neighbour) costs no second GEMM.
+//
 // Tile shape: 128 rows of A resident in shared memory per work item, B streamed in 256-column tiles, one
-// tcgen05.mma = 128 x 256 x 16.  scripts/mma_microbench.cu (B200, all SMs issuing back to back from shared
-// memory): a 128 x 128 x 16 MMA costs ~165 clk, a 128 x 256 x 16 one ~210 clk -- the instruction has a large
-// fixed cost, so N = 256 does 1.6x the flops per clock; cuBLAS bf16 on the same GPU sustains 1.36-1.63 PFLOP/s
-// (MEASURED_PEAKS.json).  B moves as a ring of four 32 KB k-blocks (256 columns x 64 k, two TMA boxes), i.e.
-// one whole tile ahead of the MMAs; the two 256-column fp32 accumulators fill TMEM.
+// tcgen05.mma = 128 x 256 x 16 (scripts/mma_microbench.cu: ~210 clk on B200, 1.6x the flops per clock of 128 x 128).
+// B moves as a ring of four 32 KB k-blocks, one whole tile ahead of the MMAs; two 256-column fp32 accumulators
+// fill TMEM.
+//
+// Epilogue (8 warps: TMEM lane quadrant x 128-column half).  The accumulator is read with tcgen05.ld.16x256b: a
+// thread then holds FOUR rows (g8, g8+8, g8+16, g8+24 of its quadrant; g8 = lane / 4) of SIXTEEN columns
+// (8n + 2q + {0,1}; q = lane % 4) per 64-column chunk.  That shape makes both reductions cheap:
+//   * rows: each thread keeps a running top-2 per row over ITS columns (4 threads x 2 halves = 8 sub-lists per row);
+//   * columns: top-2 over the thread's 4 rows in registers, then a 3-level halving butterfly across the 8 lanes that
+//     hold the other rows (28 shuffles per 64 outputs), then the 4 quadrant warps merge through shared memory.
+// Keys are 32 bits: (bits(v) << 8) | id with v in [2, 8) -- the top 8 bits of such a float are constant, so the
+// shift keeps the whole 24-bit value and frees 8 bits for the id (local column / row in block); the packing is ONE
+// integer multiply-add (IMAD, FMA pipe).  The previous kernel spent 6 of its 8 instructions per output on the ALU
+// pipe (ncu: ALU 86 % busy -- the bound); this one spends ~5.8 per output for both directions together.
+// A sub-list's second entry bounds everything it did not list, so the shortlist comes with a proved lower bound on
+// all unlisted columns (rows): k_tc_triage / k_tc_rerank use it instead of a fixed-size top-3.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNormRing = 4;  // tile gt's column norms live in slot gt % 4 (see the producer for why 4 is safe)
+constexpr uint32_t kNone24 = 0xFFFFFFu;  // 24-bit key value of "no entry" (NaN norm of a padded row / column)
+constexpr float kOffUnit = 3.25f;        // unit-norm operands: v = |x|^2 - 2 S + 3.25 in [2.2, 6.3]
+
 struct __align__(16) TcShared {
   float nrm[kNormRing][kBN];
+  uint2 colstage[2][2][4][kBN / 2];  // [tile parity][half][quadrant][column in half] -> (k0, k1) of 32 rows
   uint64_t a_full[kNumKB], a_empty;
   uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % kNormRing
   uint64_t b_full[kBSlots], b_empty[kBSlots];
@@ -227,16 +267,48 @@ struct __align__(16) TcShared {
   uint32_t tmem_base;
 };
 
-// Branch-free insertion of a packed key into the ascending triple (k0 <= k1 <= k2).
-__device__ __forceinline__ void top3_net(uint32_t x, uint32_t& k0, uint32_t& k1, uint32_t& k2) {
-  uint32_t t = min(k0, x);
-  x = max(k0, x);
-  k0 = t;
-  t = min(k1, x);
-  x = max(k1, x);
-  k1 = t;
-  k2 = min(k2, x);
+// Row sub-list of one (row, 128-column half, lane q): the two smallest keys over that thread's columns of every tile
+// as compact keys (20-bit value << 12) | column id (5-bit tile, 16 hh + 2 n + e, 2-bit q is the record index), and a
+// lower bound (20-bit value, rounded down) on every column of the sub-list that is NOT one of the two.
+// kNone20 = no entry.  Values lose their 4 low bits here (2^-18 .. 2^-17 of the key range): covered by kKeySlack.
+struct __align__(16) RowRec {
+  uint32_t k0, k1, bound, pad;
+};
+constexpr uint32_t kNone20 = 0xFFFFFu;
+// Column record of one (problem, row block, train column): the two smallest keys over the block's 128 rows,
+// (24-bit value << 8) | row in block, and the 24-bit value bounding every other row of the block from below.
+struct __align__(16) ColRec {
+  uint32_t k0, k1, bound, pad;
+};
+// Normalised shortlist handed from k_tc_triage to k_tc_rerank (unscaled: g = |b|^2 - 2 a.b as the 16-bit GEMM saw it).
+struct __align__(16) Short {
+  float g[3];
+  float bound;
+  int j[3];
+  int pad;
+};
+
+// Affine map of the key value into [2.25, 7.75]: v = (|x|^2 - 2 S) * sc + off, with |x|^2 the norm that varies along
+// the reduction (columns' for the row direction).  Unit-norm operands (the stereo pipeline) use constants.
+struct TcScale {
+  float sc, off, m2sc;
+};
+__device__ __forceinline__ TcScale tc_scale(float selfmax2, float othermax2, bool unit) {
+  TcScale t;
+  if (unit) {
+    t.sc = 1.0f;
+    t.off = kOffUnit;
+    t.m2sc = -2.0f;
+  } else {
+    const float r2 = 2.02f * sqrtf(selfmax2 * othermax2);  // |2 S| <= r2 (1.01 > (1 + 2^-9)^2: bf16 rounding)
+    const float w = fmaxf(selfmax2 + 2.0f * r2, 1e-30f);
+    t.sc = 5.5f / w;
+    t.off = 2.25f + r2 * t.sc;
+    t.m2sc = -2.0f * t.sc;
+  }
+  return t;
 }
+__device__ __forceinline__ float key_value(uint32_t v24) { return __uint_as_float(0x40000000u | v24); }
 
 // One arrival per WARP: 256 per-thread arrivals on one mbarrier serialise.
 __device__ __forceinline__ void epi_release(uint32_t bar, int lane) {
@@ -244,40 +316,77 @@ __device__ __forceinline__ void epi_release(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
-  tmem_ld32(taddr, r);
-  tmem_ld32(taddr + 32, r + 32);
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
-// Work item = (directed problem dp, 128-row block rb).  The kernel is PERSISTENT: one CTA per SM walks
-// items bid, bid + grid, ...; barriers and TMEM are set up once, and the B ring / accumulator pipelines
-// run continuously across items (global k-block and tile counters give slot and phase): the first B tile
-// of the next item is already in flight while the last MMAs of the current one retire, and the A reload
-// is consumed k-block by k-block as it lands.
+// sorted pair (a0 <= a1) <- two smallest of {a0, a1, b0, b1}, (b0 <= b1)
+__device__ __forceinline__ void merge_pairs(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
+  const uint32_t t = max(a0, b0);
+  a0 = min(a0, b0);
+  a1 = min(min(t, a1), b1);
+}
+// running pair (k0 <= k1) <- two smallest of {k0, k1, x, y}
+__device__ __forceinline__ void push_two(uint32_t& k0, uint32_t& k1, uint32_t x, uint32_t y) {
+  const uint32_t lo = min(x, y), hi = max(x, y);
+  const uint32_t t = max(k0, lo);
+  k0 = min(k0, lo);
+  k1 = min(min(t, k1), hi);
+}
+// One halving level of the column butterfly: 2*C columns held as (k0[c], k1[c]); lanes with `upper` keep columns
+// C .. 2C-1, the others 0 .. C-1; the kept columns end in slots 0 .. C-1 merged with the partner lane's lists.
+template <int C>
+__device__ __forceinline__ void col_butterfly(uint32_t* k0, uint32_t* k1, bool upper, int lane_xor) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    uint32_t m0 = upper ? k0[c + C] : k0[c], m1 = upper ? k1[c + C] : k1[c];
+    const uint32_t s0 = upper ? k0[c] : k0[c + C], s1 = upper ? k1[c] : k1[c + C];
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, lane_xor), r1 = __shfl_xor_sync(0xffffffffu, s1, lane_xor);
+    merge_pairs(m0, m1, r0, r1);
+    k0[c] = m0;
+    k1[c] = m1;
+  }
+}
+
+// 64-bit shortlist entry: (24-bit value << 32) | column; ~0 = none
+typedef unsigned long long u64k;
+__device__ __forceinline__ u64k umin64(u64k a, u64k b) { return a < b ? a : b; }
+__device__ __forceinline__ u64k umax64(u64k a, u64k b) { return a < b ? b : a; }
+// Work item = (problem p, 128-row block rb): A = the problem's queries, B = its train descriptors.  The kernel is
+// PERSISTENT: one CTA per SM walks items bid, bid + grid, ...; barriers and TMEM are set up once, and the B ring /
+// accumulator pipelines run continuously across items (global k-block and tile counters give slot and phase).
 struct TcItem {
-  int dp, rb, Na, Nb, a_op, b_op, nct;
+  int p, rb, Na, Nb, a_op, b_op, nct;
   bool valid;
 };
-__device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs, int P, int w, int nrb) {
+__device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs, int w, int nrb) {
   TcItem it;
-  it.dp = w / nrb;
-  it.rb = w - it.dp * nrb;
-  const int p = it.dp < P ? it.dp : it.dp - P;
-  const bool rev = it.dp >= P;
-  const MatchProblem pr = probs[p];
-  it.Na = rev ? pr.M : pr.N;
-  it.Nb = rev ? pr.N : pr.M;
-  it.a_op = rev ? pr.b_op : pr.a_op;
-  it.b_op = rev ? pr.a_op : pr.b_op;
+  it.p = w / nrb;
+  it.rb = w - it.p * nrb;
+  const MatchProblem pr = probs[it.p];
+  it.Na = pr.N;
+  it.Nb = pr.M;
+  it.a_op = pr.a_op;
+  it.b_op = pr.b_op;
   it.nct = (it.Nb + kBN - 1) / kBN;
   it.valid = it.rb * kBM < it.Na && it.nct > 0;
   return it;
 }
 
+template <bool kUnit, bool kCols>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs, int P,
-          const float* __restrict__ nrm, const unsigned* __restrict__ opmax, uint32_t* __restrict__ top_key,
-          int cap, uint32_t idesc, uint32_t idx_mask, int n_items) {
+k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs,
+          const float* __restrict__ nrm, const unsigned* __restrict__ opmax, RowRec* __restrict__ row_rec,
+          ColRec* __restrict__ col_rec, int cap, uint32_t idesc, int n_items, uint32_t r256) {
   extern __shared__ uint8_t smem_raw[];
   const int nrb = cap / kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,10 +427,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
     if (lane == 0) {
       uint32_t gt = 0, gk = 0, ai = 0;  // global tile / k-block counters, count of items that loaded A
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const TcItem it = tc_item(probs, P, w, nrb);
+        const TcItem it = tc_item(probs, w, nrb);
         if (!it.valid) continue;
         auto load_a = [&]() {
-          mbar_wait(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A block
+          mbar_wait_relaxed(smem_u32(&sh->a_empty), (ai & 1) ^ 1);  // previous item's MMAs no longer read the A block
           ++ai;
           const int a_row = it.a_op * cap + it.rb * kBM;
           for (int kb = 0; kb < kNumKB; ++kb) {
@@ -341,7 +450,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           const uint32_t nb_bar = smem_u32(&sh->nrm_full[gt % kNormRing]);
           for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
             const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
-            mbar_wait(smem_u32(&sh->b_empty[s]), ph ^ 1);
+            mbar_wait_relaxed(smem_u32(&sh->b_empty[s]), ph ^ 1);
             mbar_expect_tx(smem_u32(&sh->b_full[s]), kBSlotBytes);
             for (int hb = 0; hb < kBN / kBM; ++hb)  // the tensor map's box is 128 rows: two boxes per k-block
               tma_load_2d(sB + s * kBSlotBytes + hb * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB,
@@ -360,11 +469,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
     if (lane == 0) {
       uint32_t gt = 0, gk = 0, ai = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const TcItem it = tc_item(probs, P, w, nrb);
+        const TcItem it = tc_item(probs, w, nrb);
         if (!it.valid) continue;
         for (int ct = 0; ct < it.nct; ++ct, ++gt) {
           const int sa = gt % kAccStages, pha = (gt / kAccStages) & 1;
-          mbar_wait(smem_u32(&sh->acc_empty[sa]), pha ^ 1);  // epilogue drained this accumulator stage
+          mbar_wait_relaxed(smem_u32(&sh->acc_empty[sa]), pha ^ 1);  // epilogue drained this accumulator stage
           const uint32_t d = tmem_base + sa * kBN;
 #pragma unroll
           for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
@@ -389,59 +498,165 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   } else {
     // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4; 128-column half of the tile = (warp - 2) / 4 =====
     const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int q = lane & 3, g8 = lane >> 2;
     uint32_t gt = 0;
+    float na_pf[4] = {0.f, 0.f, 0.f, 0.f};  // row norms of item pf_w, fetched while the previous item was processed
+    int pf_w = -1;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const TcItem it = tc_item(probs, P, w, nrb);
+      const TcItem it = tc_item(probs, w, nrb);
       if (!it.valid) continue;
-      const int row = it.rb * kBM + quad * 32 + lane;
-      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-      const float off = key_offset(__uint_as_float(opmax[it.a_op]), __uint_as_float(opmax[it.b_op]));
-      const uint32_t nmask = ~idx_mask;
+      const float amax2 = __uint_as_float(opmax[it.a_op]), bmax2 = __uint_as_float(opmax[it.b_op]);
+      const TcScale sr = tc_scale(bmax2, amax2, kUnit);  // row direction: the column norms vary
+      const TcScale sc = tc_scale(amax2, bmax2, kUnit);  // column direction: the row norms vary
+      // this thread's four rows: row-in-block ids and the additive term of the column-direction value
+      float ca[4];
+      uint32_t rid[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        rid[m] = (uint32_t)(quad * 32 + g8 + 8 * m);
+        ca[m] = 0.f;
+        if (kCols) {
+          const float na = pf_w == w ? na_pf[m] : __ldg(nrm + (size_t)it.a_op * cap + it.rb * kBM + rid[m]);
+          ca[m] = __fmaf_rn(na, sc.sc, sc.off);
+        }
+      }
+      if (kCols) {  // start the next valid item's norm loads now: they land long before that item begins
+        pf_w = -1;
+        for (int w2 = w + gridDim.x; w2 < n_items; w2 += gridDim.x) {
+          const TcItem nx = tc_item(probs, w2, nrb);
+          if (!nx.valid) continue;
+          pf_w = w2;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) na_pf[m] = __ldg(nrm + (size_t)nx.a_op * cap + nx.rb * kBM + rid[m]);
+          break;
+        }
+      }
+      // running row lists over this thread's columns of every tile: keys + the tiles they came from
+      // rk2 = smallest key that was ever dropped from the running pair: with it, everything this thread has seen
+      // but does not list is bounded below by min(rk2, rk1 if both listed entries come from the same tile)
+      uint32_t rk0[4], rk1[4], rk2[4], rt[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        rk0[m] = rk1[m] = rk2[m] = 0xFFFFFFFFu;
+        rt[m] = 0u;
+      }
       for (int ct = 0; ct < it.nct; ++ct, ++gt) {
         const int sa = gt % kAccStages, pha = (gt / kAccStages) & 1;
         mbar_wait(smem_u32(&sh->acc_full[sa]), pha);
         tc_fence_after();
-        // the tile's column norms were bulk-copied to shared memory next to its B operand (broadcast LDS.128)
+        // the tile's column norms were bulk-copied to shared memory next to its B operand
         mbar_wait(smem_u32(&sh->nrm_full[gt % kNormRing]), (gt / kNormRing) & 1);
+        uint32_t k0[4], k1[4];  // tile-local row lists (id = 16 hh + 2 n + e: this thread's column within the tile half)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) k0[m] = k1[m] = 0xFFFFFFFFu;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int cbase = half * 128 + hh * 64;  // first column of this 64-column group within the tile
-          const int j0 = ct * kBN + cbase;
-          uint32_t acc[64];
-          tmem_ld64(tmem_base + sa * kBN + cbase + ((uint32_t)(quad * 32) << 16), acc);
-          float4 n4[16];
+          const int cbase = half * 128 + hh * 64;  // first column of this 64-column chunk within the tile
+          uint32_t acc[2][32];                     // [lane half][4 n + 2 (row pair) + e]
+          const uint32_t taddr = tmem_base + sa * kBN + cbase + ((uint32_t)(quad * 32) << 16);
+          tmem_ld_16x256b_x8(taddr, acc[0]);
+          tmem_ld_16x256b_x8(taddr + (16u << 16), acc[1]);
+          float cb[16];  // additive term of the row-direction value for this thread's 16 columns
 #pragma unroll
-          for (int e = 0; e < 16; ++e) n4[e] = *reinterpret_cast<const float4*>(&sh->nrm[gt % kNormRing][cbase + 4 * e]);
+          for (int n = 0; n < 8; ++n) {
+            const float2 nb = *reinterpret_cast<const float2*>(&sh->nrm[gt % kNormRing][cbase + 8 * n + 2 * q]);
+            cb[2 * n] = __fmaf_rn(nb.x, sr.sc, sr.off);
+            cb[2 * n + 1] = __fmaf_rn(nb.y, sr.sc, sr.off);
+          }
           tmem_ld_wait();
           if (hh == 1) {
             tc_fence_before();
             epi_release(smem_u32(&sh->acc_empty[sa]), lane);  // accumulator is in registers: release it to the MMA warp
           }
-          // tile-local shortlist first: the column-in-group index is an immediate of the packing LOP3 (one ALU op
-          // per element instead of add + LOP3); the three survivors get the column base OR-ed in afterwards
-          uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu, l2 = 0xFFFFFFFFu;
+          uint32_t c0[16], c1[16];  // column lists over this thread's four rows
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float c[4] = {n4[e].x, n4[e].y, n4[e].z, n4[e].w};
+          for (int n = 0; n < 8; ++n) {
+            uint32_t ck[4][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              // g + off > 0 for real columns; padded columns have norm = +inf -> key 0x7F8xxxxx, never selected
-              const float g = __fmaf_rn(-2.0f, __uint_as_float(acc[4 * e + u]), __fadd_rn(c[u], off));
-              const uint32_t key = (__float_as_uint(g) & nmask) | (uint32_t)(4 * e + u);
-              top3_net(key, l0, l1, l2);
+            for (int m = 0; m < 4; ++m) {
+              const float s0 = __uint_as_float(acc[m >> 1][4 * n + 2 * (m & 1)]);
+              const float s1 = __uint_as_float(acc[m >> 1][4 * n + 2 * (m & 1) + 1]);
+              // row direction: one IMAD packs value and column id; padded columns carry a NaN norm -> key 0xFFFFFFxx
+              const uint32_t ka = __float_as_uint(__fmaf_rn(s0, sr.m2sc, cb[2 * n])) * r256 + (uint32_t)(16 * hh + 2 * n);
+              const uint32_t kb = __float_as_uint(__fmaf_rn(s1, sr.m2sc, cb[2 * n + 1])) * r256 + (uint32_t)(16 * hh + 2 * n + 1);
+              push_two(k0[m], k1[m], ka, kb);
+              if (kCols) {
+                ck[m][0] = __float_as_uint(__fmaf_rn(s0, sc.m2sc, ca[m])) * 256u + rid[m];
+                ck[m][1] = __float_as_uint(__fmaf_rn(s1, sc.m2sc, ca[m])) * 256u + rid[m];
+              }
+            }
+            if (kCols) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {  // two smallest of the four rows
+                const uint32_t lo1 = min(ck[0][e], ck[1][e]), hi1 = max(ck[0][e], ck[1][e]);
+                const uint32_t lo2 = min(ck[2][e], ck[3][e]), hi2 = max(ck[2][e], ck[3][e]);
+                c0[2 * n + e] = min(lo1, lo2);
+                c1[2 * n + e] = min(min(max(lo1, lo2), hi1), hi2);
+              }
             }
           }
-          // j0 is a multiple of 64 and the local index < 64, so OR == add; 0xFFFFFFFF (empty) stays the maximum
-          top3_net(l0 | (uint32_t)j0, k0, k1, k2);
-          top3_net(l1 | (uint32_t)j0, k0, k1, k2);
-          top3_net(l2 | (uint32_t)j0, k0, k1, k2);
+          if (kCols) {
+            // across the 8 lanes that hold the other rows of the same columns (lane bits 4, 3, 2): afterwards lane L
+            // holds columns 2L, 2L+1 of the chunk, reduced over the warp's 32 rows
+            col_butterfly<8>(c0, c1, (lane & 16) != 0, 16);
+            col_butterfly<4>(c0, c1, (lane & 8) != 0, 8);
+            col_butterfly<2>(c0, c1, (lane & 4) != 0, 4);
+            *reinterpret_cast<uint4*>(&sh->colstage[gt & 1][half][quad][hh * 64 + 2 * lane]) =
+                make_uint4(c0[0], c1[0], c0[1], c1[1]);
+          }
+        }
+        // fold the tile's row lists into the running ones, remembering the tile of each entry
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const uint32_t ta0 = rt[m] & 0xFFFFu, ta1 = rt[m] >> 16;
+          const bool f = k0[m] < rk0[m];
+          const uint32_t n0 = f ? k0[m] : rk0[m], tn0 = f ? (uint32_t)ct : ta0;
+          const uint32_t x = f ? rk0[m] : k0[m], tx = f ? ta0 : (uint32_t)ct;
+          const uint32_t y = f ? k1[m] : rk1[m], ty = f ? (uint32_t)ct : ta1;
+          const uint32_t z = f ? rk1[m] : k1[m];  // second entry of the list whose first lost (z >= x)
+          const bool s = x < y;
+          rk0[m] = n0;
+          rk1[m] = s ? x : y;
+          rt[m] = tn0 | ((s ? tx : ty) << 16);
+          rk2[m] = min(rk2[m], min(max(x, y), z));  // third smallest of the four = the smallest key dropped here
+        }
+        if (kCols) {
+          // the four quadrant warps of this half merge their column lists: warp `quad` finishes 32 of the 128 columns.
+          // Two staging buffers (tile parity): a warp refills buffer b only after passing the next tile's barrier,
+          // i.e. after every warp has read tile gt's lists.
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          const int cc = 32 * quad + lane;
+          uint2 ql[4];  // (first, second) of each quadrant's 32 rows
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) ql[qq] = sh->colstage[gt & 1][half][qq][cc];
+          uint2 mine = ql[0];
+#pragma unroll
+          for (int qq = 1; qq < 4; ++qq) merge_pairs(mine.x, mine.y, ql[qq].x, ql[qq].y);
+          // every row that is not one of the two listed is >= min(smallest quadrant second, third smallest quadrant
+          // first): a quadrant's unlisted rows are >= its second, and a first that is not listed was dropped
+          const uint32_t lo1 = min(ql[0].x, ql[1].x), hi1 = max(ql[0].x, ql[1].x);
+          const uint32_t lo2 = min(ql[2].x, ql[3].x), hi2 = max(ql[2].x, ql[3].x);
+          const uint32_t third = min(min(min(ql[0].y, ql[1].y), min(ql[2].y, ql[3].y)), max(max(lo1, lo2), min(hi1, hi2)));
+          ColRec cr;
+          cr.k0 = mine.x; cr.k1 = mine.y; cr.bound = third >> 8; cr.pad = 0;
+          col_rec[((size_t)it.p * nrb + it.rb) * cap + ct * kBN + half * 128 + cc] = cr;
         }
       }
-      if (row < it.Na) {
-        uint32_t* o = top_key + (((size_t)it.dp * cap + row) * kLists + half) * kTop;
-        o[0] = k0;
-        o[1] = k1;
-        o[2] = k2;
+      // item end: one 16-byte record per (row, half, q): the thread's two best columns as compact keys and the bound on
+      // everything else it has seen (k_tc_triage merges the row's 8 sub-lists)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int row = it.rb * kBM + (int)rid[m];
+        if (row < it.Na) {
+          RowRec r;
+          const uint32_t t0 = rt[m] & 0xFFFFu, t1 = rt[m] >> 16;
+          r.k0 = ((rk0[m] >> 12) << 12) | (t0 << 5) | (rk0[m] & 31u);
+          r.k1 = ((rk1[m] >> 12) << 12) | (t1 << 5) | (rk1[m] & 31u);
+          const uint32_t b = (t0 == t1) ? min(rk2[m], rk1[m]) : rk2[m];
+          r.bound = b >> 12;  // rounded down: still a lower bound
+          r.pad = 0;
+          row_rec[(((size_t)it.p * cap + row) * 2 + half) * 4 + q] = r;
+        }
       }
     }
   }
@@ -454,17 +669,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_tc_triage: one THREAD per row.  Most rows are decided by the bound alone -- the second shortlist
-// entry is farther than the bound from the first, so the first IS the exact nearest neighbour and no
-// distance has to be evaluated (its DMatch.distance is filled in later only if the match survives).
-// Everything else (>= 2 columns inside the bound, kNN rows, tiny column counts) is queued for the
-// warp-per-row k_tc_rerank.
+// k_tc_triage: one THREAD per row of a directed problem (dp < P: query -> train from the row records; dp >= P, only
+// with cross-check: train -> query from the column records of every row block).  Merges the sub-lists into the three
+// best approximate values + a lower bound on everything unlisted, in unscaled units (g = |b|^2 - 2 a.b as the 16-bit
+// GEMM saw it).  Most rows are decided by the bound alone -- the runner-up (listed or not) is farther than the proved
+// error bound from the best, so the best IS the exact nearest neighbour and no distance has to be evaluated (its
+// DMatch.distance is filled in later only if the match survives).  Everything else is queued, with its shortlist,
+// for the warp-per-row k_tc_rerank.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void top4_insert(u64k x, u64k& e0, u64k& e1, u64k& e2, u64k& e3) {
+  u64k t;
+  t = umin64(e0, x); x = umax64(e0, x); e0 = t;
+  t = umin64(e1, x); x = umax64(e1, x); e1 = t;
+  t = umin64(e2, x); x = umax64(e2, x); e2 = t;
+  e3 = umin64(e3, x);
+}
+
 __global__ void __launch_bounds__(256)
 k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm,
-            const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
-            int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
-            int* __restrict__ rr_count, int* __restrict__ rr_list, float eps_rel, uint32_t idx_mask, float key_rel) {
+            const unsigned* __restrict__ opmax, const RowRec* __restrict__ row_rec, const ColRec* __restrict__ col_rec,
+            int cap, int max_rows, int max_cols, int* __restrict__ row_best, float* __restrict__ row_d,
+            int* __restrict__ col_best, int* __restrict__ rr_count, int* __restrict__ rr_list,
+            Short* __restrict__ shortl, float eps_rel, int unit) {
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -474,22 +700,61 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
   if (i >= Na) return;
   bool resolved = false;
   int j0 = -1;
+  Short sl;
   if (Nb == 0) {
     resolved = true;
-  } else if (Nb > kTop && !(mode == SPVO_MATCH_KNN_RATIO && !rev)) {
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
-    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+  } else {
+    // entries: (24-bit value << 32) | column; every value is widened to 24 bits (row records keep 20, rounded down)
+    u64k e0 = ~0ull, e1 = ~0ull, e2 = ~0ull, e3 = ~0ull;
+    uint32_t bound = kNone24;
+    if (!rev) {
+      const uint4* rec = reinterpret_cast<const uint4*>(row_rec + ((size_t)p * cap + i) * 8);
 #pragma unroll
-    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
-    const float na = nrm[(size_t)a_op * cap + i];
+      for (int sl8 = 0; sl8 < 8; ++sl8) {  // sub-list = (half, q)
+        const uint4 r = __ldg(rec + sl8);
+        const int hf = sl8 >> 2, q = sl8 & 3;
+        const uint32_t kk[2] = {r.x, r.y};
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          if ((kk[z] >> 12) < kNone20) {
+            const uint32_t id = kk[z] & 31u, tile = (kk[z] >> 5) & 31u;
+            const uint32_t col = tile * kBN + hf * 128 + (id >> 4) * 64 + ((id >> 1) & 7) * 8 + 2 * q + (id & 1);
+            top4_insert(((u64k)((kk[z] >> 12) << 4) << 32) | col, e0, e1, e2, e3);
+          }
+        }
+        if (r.z < kNone20) bound = min(bound, r.z << 4);
+      }
+    } else {
+      const int nrb = cap / kBM, nrbv = (pr.N + kBM - 1) / kBM;  // row blocks of the forward problem that exist
+      for (int rb = 0; rb < nrbv; ++rb) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(col_rec + ((size_t)p * nrb + rb) * cap + i));
+        if ((c.x >> 8) < kNone24) top4_insert(((u64k)(c.x >> 8) << 32) | (uint32_t)(rb * kBM + (c.x & 0xFFu)), e0, e1, e2, e3);
+        if ((c.y >> 8) < kNone24) top4_insert(((u64k)(c.y >> 8) << 32) | (uint32_t)(rb * kBM + (c.y & 0xFFu)), e0, e1, e2, e3);
+        bound = min(bound, min(kNone24, c.z));  // rows of this block beyond its two listed ones
+      }
+    }
+    bound = min(bound, (uint32_t)min((u64k)kNone24, e3 >> 32));  // listed, but beyond the three kept
+    if (Nb <= kTop) bound = kNone24;                              // the list is the whole row
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
-    const float off = key_offset(amax, bmax);
-    const float g0 = __uint_as_float(k0 & ~idx_mask) - off, g1 = __uint_as_float(k1 & ~idx_mask) - off;
-    const float eps = eps_rel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
-    const float slack = 2.0f * eps + key_rel * (g0 + 2.0f * eps + off) * 1.01f;
-    if (g1 > g0 + slack) {  // same test as k_tc_rerank's nc == 1
-      resolved = true;
-      j0 = (int)(k0 & idx_mask);
+    const TcScale ts = tc_scale(bmax, amax, unit != 0);  // the reduction ran over the B side's norms
+    const float inv = 1.0f / ts.sc;
+    const u64k ee[3] = {e0, e1, e2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const bool ok = ee[k] != ~0ull;
+      sl.g[k] = ok ? (key_value((uint32_t)(ee[k] >> 32)) - ts.off) * inv : INFINITY;
+      sl.j[k] = ok ? (int)(uint32_t)ee[k] : -1;
+    }
+    sl.bound = bound < kNone24 ? (key_value(bound) - ts.off) * inv : INFINITY;
+    sl.pad = 0;
+    if (!(mode == SPVO_MATCH_KNN_RATIO && !rev) && sl.j[0] >= 0) {
+      const float na = nrm[(size_t)a_op * cap + i];
+      const float eps = eps_rel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
+      const float slack = 2.0f * eps + kKeySlack * inv;
+      if (fminf(sl.g[1], sl.bound) > sl.g[0] + slack) {  // same test as k_tc_rerank's "one candidate, complete"
+        resolved = true;
+        j0 = sl.j[0];
+      }
     }
   }
   if (resolved) {
@@ -503,7 +768,9 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
       col_best[(size_t)p * max_cols + i] = j0;
     }
   } else {
-    rr_list[(size_t)dp * cap + atomicAdd(&rr_count[dp], 1)] = i;
+    const int slot = atomicAdd(&rr_count[dp], 1);
+    rr_list[(size_t)dp * cap + slot] = i;
+    shortl[(size_t)dp * cap + slot] = sl;
   }
 }
 
@@ -541,11 +808,10 @@ __device__ __forceinline__ void top2_push(float d, int j, float& b0, int& x0, fl
 
 __global__ void __launch_bounds__(256)
 k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
-            const unsigned* __restrict__ opmax, const uint32_t* __restrict__ top_key, int cap, int max_rows,
+            const unsigned* __restrict__ opmax, const Short* __restrict__ shortl, int cap, int max_rows,
             int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
             int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
-            float eps_rel, uint32_t idx_mask, float key_rel, const int* __restrict__ rr_count,
-            const int* __restrict__ rr_list) {
+            float eps_rel, int unit, const int* __restrict__ rr_count, const int* __restrict__ rr_list) {
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -564,44 +830,35 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   const float* arow = A + (size_t)i * kDim;
   (void)Na;
   if (Nb > 0) {
-    // merge the two per-half shortlists: the kTop smallest packed keys of the row
-    const uint32_t* kp = top_key + ((size_t)dp * cap + i) * kLists * kTop;
-    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-#pragma unroll
-    for (int e = 0; e < kLists * kTop; ++e) top3_net(kp[e], k0, k1, k2);
+    // the row's shortlist as k_tc_triage normalised it: three best approximate values, their columns, and a lower
+    // bound on every column that is not listed
+    const Short sl = shortl[(size_t)dp * cap + li];
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
-    const float off = key_offset(amax, bmax);
-    const uint32_t kk[kTop] = {k0, k1, k2};
-    float g[kTop];
-    int jx[kTop];
-#pragma unroll
-    for (int k = 0; k < kTop; ++k) {
-      g[k] = __uint_as_float(kk[k] & ~idx_mask) - off;   // truncated: true value in [g, g + key_rel*(g+off))
-      jx[k] = (int)(kk[k] & idx_mask);
-    }
-    // bound on |approx - exact| of any relevant column of this row, plus the key truncation
+    const TcScale ts = tc_scale(bmax, amax, unit != 0);
+    const float g[kTop] = {sl.g[0], sl.g[1], sl.g[2]};
+    const int jx[kTop] = {sl.j[0], sl.j[1], sl.j[2]};
+    // bound on |approx - exact| of any relevant column of this row, plus the rounding of the key arithmetic
     const float eps = eps_rel * sqrtf(na * bmax) + kEpsAbs * (na + bmax);
     const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
-    const float ref = knn ? g[1] : g[0];
-    const float slack = 2.0f * eps + key_rel * (ref + 2.0f * eps + off) * 1.01f;
+    const float slack = 2.0f * eps + kKeySlack / ts.sc;
     int nc;
-    if (Nb <= kTop) {
-      nc = Nb;  // the shortlist is the whole row
-    } else if (!knn) {
+    if (!knn) {
+      // candidates = listed columns within the bound of the best; complete iff every unlisted column is outside it
       nc = 1;
-      while (nc < kTop && g[nc] <= g[0] + slack) ++nc;
-      if (nc == kTop) full = true;  // the third entry is still within the bound: cannot prove completeness
+      while (nc < kTop && jx[nc] >= 0 && g[nc] <= g[0] + slack) ++nc;
+      if (!(sl.bound > g[0] + slack)) full = true;
+    } else if (jx[1] < 0) {
+      nc = 1;  // a single train column: the second best does not exist (the ratio test then fails in finalize)
     } else {
       nc = 2;
-      while (nc < kTop && g[nc] <= g[1] + slack) ++nc;
-      if (nc == kTop) {
+      while (nc < kTop && jx[nc] >= 0 && g[nc] <= g[1] + slack) ++nc;
+      if (!(sl.bound > g[1] + slack)) {
         // exact second best unknown; the ratio decision may still be provable from the bound
-        const float slack0 = 2.0f * eps + key_rel * (g[0] + 2.0f * eps + off) * 1.01f;
-        if (g[1] > g[0] + slack0) {
+        if (fminf(g[1], sl.bound) > g[0] + slack) {
           const float d0 = exact_dist_half(arow, B + (size_t)jx[0] * kDim, l16);
-          const float lo2 = g[1] + na - eps;                                     // exact second best d^2 >= lo2
-          const float hi2 = g[1] + na + eps + key_rel * (g[1] + off) * 1.01f;    // and <= hi2
+          const float lo2 = fminf(g[1], sl.bound) + na - eps - kKeySlack / ts.sc;  // exact second best d^2 >= lo2
+          const float hi2 = g[1] + na + eps + kKeySlack / ts.sc;                    // and <= hi2 (column jx[1] exists)
           const float lo = sqrtf(fmaxf(lo2, 0.0f)) * (1.0f - 1e-6f);
           const float hi = sqrtf(fmaxf(hi2, 0.0f)) * (1.0f + 1e-6f);
           if (d0 < ratio * lo) {  // passes for any admissible second best
@@ -894,7 +1151,10 @@ struct TcWorkspace {
   __nv_bfloat16* xb = nullptr;
   float* nrm = nullptr;
   unsigned* opmax = nullptr;
-  uint32_t* top_key = nullptr;
+  RowRec* row_rec = nullptr;   // [P][cap][2 halves][4 lanes]
+  ColRec* col_rec = nullptr;   // [P][cap / 128 row blocks][cap]
+  Short* shortl = nullptr;     // [ndir][cap] shortlists of the rows k_tc_triage queued
+  size_t rec_rows = 0, rec_cols = 0;  // capacities of row_rec (rows) and col_rec (elements)
   int* fb_list = nullptr;
   int* rr_count = nullptr;  // rows queued by k_tc_triage for k_tc_rerank
   int* rr_list = nullptr;
@@ -904,7 +1164,7 @@ struct TcWorkspace {
   CUtensorMap tmap;
 };
 
-static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, size_t ndir) {
+static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, size_t ndir, size_t nprob) {
   const size_t rows = ops * cap;
   cudaError_t e;
   if (w->rows < rows || w->ops < ops) {
@@ -927,18 +1187,28 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
     w->rows = rows;
     w->ops = ops;
   }
+  const size_t rec_rows = nprob * cap, rec_cols = nprob * (cap / kBM) * cap;
+  if (w->rec_rows < rec_rows || w->rec_cols < rec_cols) {
+    if (w->row_rec) cudaFree(w->row_rec);
+    if (w->col_rec) cudaFree(w->col_rec);
+    w->row_rec = nullptr; w->col_rec = nullptr; w->rec_rows = 0; w->rec_cols = 0;
+    const size_t rr = rec_rows > w->rec_rows ? rec_rows : w->rec_rows, rc = rec_cols > w->rec_cols ? rec_cols : w->rec_cols;
+    if ((e = cudaMalloc((void**)&w->row_rec, rr * 8 * sizeof(RowRec))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->col_rec, rc * sizeof(ColRec))) != cudaSuccess) return e;
+    w->rec_rows = rr; w->rec_cols = rc;
+  }
   const size_t top_rows = ndir * cap;
   if (w->top_rows < top_rows) {
-    if (w->top_key) cudaFree(w->top_key);
+    if (w->shortl) cudaFree(w->shortl);
     if (w->fb_list) cudaFree(w->fb_list);
     if (w->rr_count) cudaFree(w->rr_count);
     if (w->rr_list) cudaFree(w->rr_list);
-    w->top_key = nullptr; w->fb_list = nullptr; w->rr_count = nullptr; w->rr_list = nullptr;
+    w->shortl = nullptr; w->fb_list = nullptr; w->rr_count = nullptr; w->rr_list = nullptr;
     w->top_rows = 0;
     if ((e = cudaMalloc((void**)&w->rr_count, 2 * top_rows * sizeof(int))) != cudaSuccess) return e;  // + the fallback counters
     if ((e = cudaMalloc((void**)&w->rr_list, top_rows * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&w->fb_list, top_rows * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&w->top_key, top_rows * kLists * kTop * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&w->shortl, top_rows * sizeof(Short))) != cudaSuccess) return e;
     w->top_rows = top_rows;
   }
   return cudaSuccess;
@@ -947,7 +1217,7 @@ static cudaError_t tc_ensure(Handle* h, TcWorkspace* w, size_t ops, size_t cap, 
 void tc_workspace_free(Handle* h) {
   TcWorkspace* w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
   if (!w) return;
-  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->top_key, w->fb_list, w->rr_count, w->rr_list};
+  void* ptrs[] = {w->xb, w->nrm, w->opmax, w->row_rec, w->col_rec, w->shortl, w->fb_list, w->rr_count, w->rr_list};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete w;
@@ -958,16 +1228,16 @@ cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, in
                                  const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride);
 cudaError_t ensure_select_buffers(Handle* h, int P, int mr, int mc);
 
-static cudaError_t tc_get(Handle* h, TcWorkspace** w, size_t ops, size_t cap, size_t ndir) {
+static cudaError_t tc_get(Handle* h, TcWorkspace** w, size_t ops, size_t cap, size_t ndir, size_t nprob) {
   if (!h->tc_ws) h->tc_ws = new TcWorkspace();
   *w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
-  return tc_ensure(h, *w, ops, cap, ndir);
+  return tc_ensure(h, *w, ops, cap, ndir, nprob);
 }
 
 cudaError_t tc_prepare_slots(Handle* h, int slots, int max_rows, int ndir, TcSink* sink) {
   TcWorkspace* w;
   const int cap = (max_rows + kCapAlign - 1) / kCapAlign * kCapAlign;
-  cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir);
+  cudaError_t e = tc_get(h, &w, (size_t)slots, (size_t)cap, (size_t)ndir, (size_t)(ndir + 1) / 2);
   if (e != cudaSuccess) return e;
   w->slot_cap = cap;
   w->fp16 = true;  // decode's descriptors are unit-norm (NN:428): fp16 is range-safe and 8x finer than bf16
@@ -1014,13 +1284,15 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     if (operands_ready) {
       // the stereo pipeline already reserved the slots and k_desc_normalize filled them
       w = reinterpret_cast<TcWorkspace*>(h->tc_ws);
-      if (!w || w->top_rows < (size_t)ndir * w->slot_cap) return cudaErrorInvalidValue;
+      if (!w || w->top_rows < (size_t)ndir * w->slot_cap || w->rec_rows < (size_t)P * w->slot_cap ||
+          w->rec_cols < (size_t)P * (w->slot_cap / kBM) * w->slot_cap)
+        return cudaErrorInvalidValue;
       cap = w->slot_cap;
     } else {
       // operand slots are the problems' a_op / b_op: 2p, 2p+1 for the generic entry points, image indices (and the
       // carry slot max_batch) for a stereo batch whose decode could not fill them
       const size_t ops = (size_t)(2 * P > h->max_batch + 1 ? 2 * P : h->max_batch + 1);
-      if ((e = tc_get(h, &w, ops, (size_t)cap, (size_t)ndir)) != cudaSuccess) return e;
+      if ((e = tc_get(h, &w, ops, (size_t)cap, (size_t)ndir, (size_t)P)) != cudaSuccess) return e;
       w->slot_cap = cap;
       w->fp16 = false;  // arbitrary CV_32F descriptors: bf16 keeps the fp32 exponent range
       h->carry_tc_valid = false;  // the slots (and possibly the buffers) of a previous stereo batch are overwritten
@@ -1031,33 +1303,33 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     // one memset for both worklist counters: fb_count sits right behind the ndir rerank counters of this call
     int* const fb_count = w->rr_count + ndir;
     if ((e = cudaMemsetAsync(w->rr_count, 0, (size_t)2 * ndir * sizeof(int), st)) != cudaSuccess) return e;
-    int idx_bits = 7;
-    while ((1 << idx_bits) < cap) ++idx_bits;
-    if (idx_bits > kMaxIdxBits) return cudaErrorInvalidValue;
-    const uint32_t idx_mask = (1u << idx_bits) - 1u;
-    const float key_rel = 1.0f / (float)(1u << (23 - idx_bits));
     const float eps_rel = w->fp16 ? kEpsRelFp16 : kEpsRelBf16;
+    // unit-norm operands (written by decode, fp16) use constant key scaling; arbitrary CV_32F inputs scale by the
+    // operands' largest norms (tc_scale)
+    const int unit = (operands_ready && w->fp16) ? 1 : 0;
     const size_t smem = 1024 + (size_t)kNumKB * kTileBytes + (size_t)kBSlots * kBSlotBytes + sizeof(TcShared);
-    if ((e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     {
+      auto kern = cross ? (unit ? k_tc_gemm<true, true> : k_tc_gemm<false, true>)
+                        : (unit ? k_tc_gemm<true, false> : k_tc_gemm<false, false>);
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       LaunchScope ls(h, KID_TC_GEMM);
-      const int n_items = (cap / kBM) * ndir;
+      const int n_items = (cap / kBM) * P;  // ONE Gram matrix per problem: both directions come from its epilogue
       const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
-      k_tc_gemm<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, P, w->nrm, w->opmax, w->top_key, cap,
-                                                make_idesc(w->fp16), idx_mask, n_items);
+      kern<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, w->nrm, w->opmax, w->row_rec, w->col_rec, cap,
+                                           make_idesc(w->fp16), n_items, 256u);
     }
     {
       LaunchScope ls(h, KID_TC_TRIAGE);
-      k_tc_triage<<<dim3((cap + 255) / 256, ndir), 256, 0, st>>>(probs, P, cfg.mode, w->nrm, w->opmax, w->top_key, cap,
-                                                               mr, mc, h->row_best, h->row_d, h->col_best, w->rr_count,
-                                                               w->rr_list, eps_rel, idx_mask, key_rel);
+      k_tc_triage<<<dim3((cap + 255) / 256, ndir), 256, 0, st>>>(probs, P, cfg.mode, w->nrm, w->opmax, w->row_rec,
+                                                               w->col_rec, cap, mr, mc, h->row_best, h->row_d,
+                                                               h->col_best, w->rr_count, w->rr_list, w->shortl, eps_rel,
+                                                               unit);
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
-      k_tc_rerank<<<dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir), 256, 0, st>>>(probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->top_key,
-                                                     cap, mr, mc, h->row_best, h->row_d, h->col_best, fb_count,
-                                                     w->fb_list, h->counters, eps_rel, idx_mask, key_rel, w->rr_count,
-                                                     w->rr_list);
+      k_tc_rerank<<<dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir), 256, 0, st>>>(
+          probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->shortl, cap, mr, mc, h->row_best, h->row_d, h->col_best,
+          fb_count, w->fb_list, h->counters, eps_rel, unit, w->rr_count, w->rr_list);
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
