@@ -206,8 +206,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "stereo_frame_pairs_per_sec_decode_match", "value": val, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": step_pairs, "H": H, "W": W, "keypoints": K,
+        "config": {"workload": WORKLOAD, "pairs_per_step": args.pairs_per_step, "H": H, "W": W, "keypoints": K,
                    "match": "nn_crosscheck"},
+        "reference_sample_pairs_per_step": step_pairs,
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -321,6 +322,152 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * args.steps * F / float(t.item())
 
+    # ---------------- H2D ceiling: the same pinned buffers copied by all ranks at once, no kernels ----------------
+    # (e2e is PCIe / host-memory bound: this measures the platform limit instead of asserting it)
+    d_semi_probe, d_desc_probe = semi[0], desc[0]
+    cs = torch.cuda.Stream(device=dev)
+    barrier()
+    with torch.cuda.stream(cs):
+        for _ in range(2):
+            d_semi_probe.copy_(h_semi[0], non_blocking=True)
+            d_desc_probe.copy_(h_desc[0], non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    n_probe = 4
+    with torch.cuda.stream(cs):
+        for i in range(n_probe):
+            d_semi_probe.copy_(h_semi[0], non_blocking=True)
+            d_desc_probe.copy_(h_desc[0], non_blocking=True)
+    torch.cuda.synchronize()
+    probe_s = time.perf_counter() - t0
+    tp = torch.tensor([probe_s], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    h2d_ceiling_gbs = n_probe * in_bytes / float(tp.item()) / 1e9       # per rank, all ranks copying concurrently
+    h2d_gbs = args.steps * in_bytes / float(t.item()) / 1e9              # what the e2e call achieved per rank
+    del h_semi, h_desc
+
+    # ---------------- BASELINE config 3: K = 2048, kNN-2 + 0.8 ratio test, frame-sharded like the primary ----------------
+    K3, F3 = 2048, args.pairs_per_step // 2
+    fe3 = S.Frontend(local_rank, 2 * F3, H, W, K3)
+    fe3.set_stream(stream.cuda_stream)
+    out3 = fe3.alloc_stereo_out(F3, K3, device=dev)
+    cfg3 = dict(max_keypoints=K3, mode=S.MATCH_KNN_RATIO, ratio=0.8, stereo_threshold=2.0, min_disparity=0.25)
+    semi3 = semi.view(R * F, 2, 65, H // 8, W // 8)
+    desc3 = desc.view(R * F, 2, 256, H // 8, W // 8)
+    nb3 = (R * F) // F3
+
+    def step3(i):
+        b = i % nb3
+        fe3.stereo_batch_device(semi3[b * F3:(b + 1) * F3], desc3[b * F3:(b + 1) * F3], F3, H, W, out3, **cfg3)
+
+    steps3 = max(10, args.steps // 4)
+    fe3.stereo_reset()
+    for i in range(3):
+        step3(i)
+    barrier()
+    e0.record(stream)
+    for i in range(steps3):
+        step3(3 + i)
+    e1.record(stream)
+    barrier()
+    t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    config3 = {"workload": "kitti_synth_1240x376_K2048_knn_ratio0.8_stereo+temporal", "value": world * steps3 * F3 / (float(t3.item()) * 1e-3),
+               "unit": "pairs/s", "pairs_per_step": F3, "steps": steps3, "ms_per_step": float(t3.item()) / steps3,
+               "mean_keypoints": out3["n_kpts"].float().mean().item(), "mean_matches": out3["n_matches"].float().mean().item(),
+               "scaling": "weak", "timing": "device-resident, CUDA events, max over ranks"}
+    fe3.close()
+    del out3
+
+    # ---------------- strong scaling: the WHOLE 4541-frame sequence, sharded with a one-frame halo, lists gathered ----------------
+    import spvo_b200.sequence as seq
+    shards = seq.plan_shards(SEQ_LEN, world)
+    first_f, count_f = shards[rank]
+    nbatch = (max(c for _, c in shards) + F - 1) // F  # the same on every rank: equal-sized gather contributions
+    list_keys = ("kpts", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")
+    slabs = [fe.alloc_stereo_out(F, K, device=dev, with_desc=False) for _ in range(nbatch)]
+    desc_scratch = out["desc"]
+    halo_out = fe.alloc_stereo_out(1, K, device=dev)
+    host_bufs = {}
+    if rank == 0:  # pinned landing buffers for the gathered lists (allocated once, outside the timed region)
+        for k in list_keys:
+            host_bufs[k] = torch.empty(world * nbatch * slabs[0][k].numel(), dtype=slabs[0][k].dtype, pin_memory=True)
+
+    def process(first_frame, count, reset):
+        if reset:
+            fe.stereo_reset()
+        if count == 1 and first_frame < first_f:  # the halo frame: results dropped
+            o = halo_out
+        else:
+            o = dict(slabs[(first_frame - first_f) // F])
+            o["desc"] = desc_scratch
+        r = (first_frame // F) % R  # synthetic inputs cycle through the resident ring (generation is not timed)
+        fe.stereo_batch_device(semi[r][:count], desc[r][:count], count, H, W, o, **cfg)
+        return range(count)
+
+    def run_sequence():
+        seq.run_shard(process, first_f, count_f, F, halo=True)
+        # gather: every rank's lists to rank 0 (device -> device over NVLink), then one copy per list to the host there
+        for k in list_keys:
+            mine = torch.cat([s_[k].reshape(-1) for s_ in slabs])
+            if world > 1:
+                parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+                dist.gather(mine, parts, dst=0)
+                if rank == 0:
+                    mine = torch.cat(parts)
+            if rank == 0:
+                host_bufs[k].copy_(mine, non_blocking=True)
+        torch.cuda.synchronize()
+
+    run_sequence()  # warm-up (allocator, NCCL channels)
+    barrier()
+    t0 = time.perf_counter()
+    run_sequence()
+    if world > 1:
+        dist.barrier()
+    strong_s = time.perf_counter() - t0
+    ts = torch.tensor([strong_s], device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    strong = {"workload": WORKLOAD, "frames": SEQ_LEN, "value": SEQ_LEN / float(ts.item()), "unit": "pairs/s",
+              "seconds": float(ts.item()), "scaling": "strong", "batches_per_rank": nbatch,
+              "what": "whole sequence through sequence.run_shard (contiguous frame ranges, one-frame halo, "
+                      "spvo_stereo_reset per shard), keypoint / match / map / quadruple lists gathered to rank 0 "
+                      "(NCCL gather) and copied to the host; wall clock, max over ranks; inputs device-resident"}
+    del slabs, host_bufs
+
+    # ---------------- BASELINE config 4: 640x192, K = 500, ONE pair per call (the reference's real-time shape) ----------------
+    H4, W4, K4 = 192, 640, 500
+    s4, d4 = synth.make_stream(32, H4, W4, seed=2, device=dev)
+    fe4 = S.Frontend(local_rank, 2, H4, W4, K4)
+    fe4.set_stream(stream.cuda_stream)
+    out4 = fe4.alloc_stereo_out(1, K4, device=dev)
+    cfg4 = dict(max_keypoints=K4, mode=S.MATCH_NN_CROSSCHECK, stereo_threshold=2.0, min_disparity=0.25)
+    lat = {}
+    for name, kw in (("plain_launches", {}), ("library_graph", {"graph": True})):
+        try:
+            fe4.stereo_reset()
+            for i in range(8):
+                fe4.stereo_batch_device(s4[i % 32], d4[i % 32], 1, H4, W4, out4, **cfg4, **kw)
+            torch.cuda.synchronize()
+            n4 = 200
+            e0.record(stream)
+            for i in range(n4):
+                fe4.stereo_batch_device(s4[i % 32], d4[i % 32], 1, H4, W4, out4, **cfg4, **kw)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            lat[name + "_us_per_pair"] = 1e3 * e0.elapsed_time(e1) / n4
+        except TypeError:
+            lat[name + "_us_per_pair"] = None
+    latency = {"workload": "640x192_K500_nn_crosscheck_one_pair_per_call", **lat,
+               "roofline_us": 5.98e6 / (peaks["hbm"] * 1e9) * 1e6,
+               "timing": "200 back-to-back calls, CUDA events on the launching stream (device time per call)"}
+    fe4.close()
+
     if rank == 0:
         # ---------------- roofline of the dominant kernel ----------------
         cells = (H // 8) * (W // 8)
@@ -349,6 +496,18 @@ def run_ours(args, rank, world, local_rank):
             ach, peak, unit = work / dur / 1e12, peaks["tf_sus"], "TFLOP/s"
         roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                     "traffic": traffic, "peak_source": peaks["src"] + (" (sustained)" if bound == "tensor" else "")}
+        tensor_roofline = None
+        if "k_tc_gemm" in prof:
+            tdur = prof["k_tc_gemm"][0] / prof["k_tc_gemm"][1] * 1e-3
+            cap_rows = (K + 255) // 256 * 256
+            alg_fl = 2 * F * 2.0 * n_kp * n_kp * 256        # one Gram matrix per match
+            exe_fl = 2 * F * 2.0 * cap_rows * cap_rows * 256  # what the tensor pipe executes (rows / columns padded to 256)
+            tensor_roofline = {"kernel": "k_tc_gemm", "bound": "tensor", "ms_per_launch": tdur * 1e3,
+                               "achieved": alg_fl / tdur / 1e12, "executed": exe_fl / tdur / 1e12, "unit": "TFLOP/s",
+                               "peak": peaks["tf_sus"], "peak_burst": peaks["tf_burst"], "frac": alg_fl / tdur / 1e12 / peaks["tf_sus"],
+                               "frac_of_burst": alg_fl / tdur / 1e12 / peaks["tf_burst"],
+                               "note": "algorithmic flops = 2*N*M*256 per match, one Gram matrix serves both directions of "
+                                       "the cross-check; peak = measured cuBLAS bf16 (sustained / burst)"}
         dec_ms = sum(prof[k][0] for k in ("k_softmax_heat", "k_detect", "k_sample_desc", "k_desc_planes", "k_desc_normalize") if k in prof) / args.steps
         dec_bytes = B * (4 * (65 + 256) * cells + K * 1052)
         decode_roofline = {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
@@ -373,11 +532,18 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs cycle through a ring of {R} batches x {in_bytes / 1e6:.0f} MB (> 126 MB L2)",
                        "frame_sharding": f"{world} contiguous ranges of {shard} frames",
                        "mean_keypoints": n_kp, "mean_matches": n_m},
-            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "h2d_gbs": h2d_gbs, "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                    "note": "per rank: GB/s of input the e2e call moved, and what the same pinned buffers reach when every "
+                            "rank only copies (no kernels) -- the platform's H2D ceiling at this rank count"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": roofline,
             "decode_roofline": decode_roofline,
+            "tensor_roofline": tensor_roofline,
+            "config3": config3,
+            "strong": strong,
+            "latency": latency,
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
         }))

@@ -245,6 +245,12 @@ long long spvo_kernel_launches(spvo_handle h);
  * Cumulative since spvo_create. */
 int spvo_debug_counters(spvo_handle h, long long* out, int n);
 
+/* Self-check of k_softmax_heat's shared-reciprocal division (tests only): a_bits / b_bits are DEVICE arrays of n fp32
+ * bit patterns; *mismatches = operand pairs (inside the kernel's guarded domain) whose quotient differs from the IEEE
+ * division the reference performs (NN:280-284).  Must be 0. */
+int spvo_debug_div_check(spvo_handle h, const uint32_t* a_bits, const uint32_t* b_bits, long long n,
+                         long long* mismatches);
+
 /* Optional per-kernel profile: when enabled every kernel launch is bracketed by CUDA events on
  * the handle's stream (how bench.py measures the dominant kernel's duration live, inside its timed
  * region).  spvo_profile_read synchronises the stream, returns the accumulated milliseconds and

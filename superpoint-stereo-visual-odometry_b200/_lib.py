@@ -47,7 +47,7 @@ SYMBOLS = [
     "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
     "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch",
     "spvo_decode_f16", "spvo_decode_device_f16", "spvo_stereo_batch_f16", "spvo_stereo_batch_device_f16",
-    "spvo_kernel_launches", "spvo_debug_counters", "spvo_profile_enable", "spvo_profile_num_kernels",
+    "spvo_kernel_launches", "spvo_debug_counters", "spvo_debug_div_check", "spvo_profile_enable", "spvo_profile_num_kernels",
     "spvo_profile_kernel_name", "spvo_profile_read",
 ]
 
@@ -92,6 +92,8 @@ def load():
     L.spvo_kernel_launches.restype = C.c_longlong
     L.spvo_kernel_launches.argtypes = [vp]
     L.spvo_debug_counters.argtypes = [vp, vp, ci]
+    L.spvo_debug_div_check.argtypes = [vp, vp, vp, C.c_longlong, C.POINTER(C.c_longlong)]
+    L.spvo_debug_div_check.restype = ci
     L.spvo_profile_enable.argtypes = [vp, ci]
     L.spvo_profile_enable.restype = ci
     L.spvo_profile_num_kernels.restype = ci

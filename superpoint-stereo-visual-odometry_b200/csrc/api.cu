@@ -11,6 +11,7 @@
 
 namespace spvo {
 size_t decode_smem_required(int H, int W, int K);
+size_t decode_list_bytes_per_image();
 }
 
 using namespace spvo;
@@ -99,7 +100,7 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   }
   h->stream = h->own_stream;
   ALLOC(h->heat, (size_t)max_batch * px * sizeof(float));
-  ALLOC(h->hist, (size_t)max_batch * kHistBins * sizeof(unsigned));
+  ALLOC(h->cand_list, (size_t)max_batch * decode_list_bytes_per_image());
   ALLOC(h->cellmax, (size_t)max_batch * cells * sizeof(uint2));
   ALLOC(h->nms_bitmap, (size_t)max_batch * (px / 16 + 64) * sizeof(unsigned));  // H*ceil(W/32) <= H*W/16 for W >= 16
   ALLOC(h->counters, 8 * sizeof(unsigned long long));
@@ -126,7 +127,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->hist, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->cand_list, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
@@ -721,6 +722,22 @@ int spvo_profile_read(spvo_handle hh, double* ms, long long* launches, int n) {
     h->prof_ms[i] = 0;
     h->prof_n[i] = 0;
   }
+  return SPVO_OK;
+}
+
+int spvo_debug_div_check(spvo_handle hh, const uint32_t* a_bits, const uint32_t* b_bits, long long n,
+                         long long* mismatches) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !a_bits || !b_bits || !mismatches || n < 0) return SPVO_EINVAL;
+  DeviceGuard g(h->device);
+  unsigned long long* d = h->counters + 7;  // the last counter slot is scratch for this check
+  CK(cudaMemsetAsync(d, 0, sizeof(*d), h->stream));
+  CK(launch_div_check(h, a_bits, b_bits, n, d));
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemsetAsync(d, 0, sizeof(*d), h->stream));
+  *mismatches = (long long)v;
   return SPVO_OK;
 }
 

@@ -12,7 +12,7 @@
 
 namespace spvo {
 
-// Sampled score histogram used to pick the first candidate chunk (decode.cu).
+// Score bins used to size k_detect's candidate chunks (decode.cu).
 // bin(v) = (bits(1.0f) - bits(v)) >> 14, clamped to [0, 4095]; bin 0 holds the highest scores.
 constexpr int kHistBins = 4096;
 constexpr int kHistShift = 14;
@@ -54,6 +54,8 @@ struct TcSink {
 cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_f16, int B, int H, int W,
                           const spvo_decode_cfg& cfg, spvo_keypoint* kpts, float* desc_out, int* n_out,
                           float* scores, const TcSink* sink = nullptr, bool* sink_filled = nullptr);
+cudaError_t launch_div_check(Handle* h, const uint32_t* a_bits, const uint32_t* b_bits, long long n,
+                             unsigned long long* mismatches);
 // ---- match.cu ----
 cudaError_t launch_match_exact(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                                const spvo_match_cfg& cfg, spvo_dmatch* out, int* n_matches, int* q2t,
@@ -99,7 +101,7 @@ struct Handle {
   int max_batch = 0, max_h = 0, max_w = 0, max_k = 0;
   // decode workspace
   float* heat = nullptr;          // [max_batch, max_h*max_w]
-  unsigned* hist = nullptr;       // [max_batch, kHistBins]
+  unsigned long long* cand_list = nullptr;  // [max_batch, kListCap] candidate keys of k_detect's current generation
   uint2* cellmax = nullptr;       // [max_batch, cells] per-cell (max, second max | argmax) records of the heatmap
   unsigned* nms_bitmap = nullptr; // [max_batch, max_h*ceil(max_w/32)] suppression bitmap of the multi-chunk path
   float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)

@@ -3,7 +3,8 @@
 // Replaces SuperPointFeatureFrontEnd::postprocessDetectionAndDescription() and its helpers
 // (reference: src/odml_visual_odometry/src/feature_detection_neural_network.cpp, "NN" below):
 //   k_softmax_heat  NN:266-326  exp, channel sum (c = 0..64 in order), /(sum + 1e-5), dustbin drop,
-//                               depth-to-space to the H x W heatmap; plus a sampled score histogram.
+//                               depth-to-space to the H x W heatmap; plus a per-cell (max, second max, argmax)
+//                               record from which k_detect finds its candidates without scanning the heatmap.
 //   k_detect        NN:188-262  strict '>' threshold, descending-score order with the canonical
 //                               tie-break (score desc, x asc, y asc), greedy box NMS, border filter,
 //                               stop at K emitted.  Exact: candidates are consumed in descending key
@@ -38,10 +39,24 @@ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 //     contiguous.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHeatThreads = 128;
+
+// e / denom, correctly rounded (== __fdiv_rn, the oracle's `/`), from ONE reciprocal per cell.  Markstein's
+// sequence: with y = RN(1/b), q0 = RN(a y) is within 1.5 ulp of a/b; q1 = RN(q0 + RN(a - b q0) y) is a faithful
+// quotient (the remainder is exact in an FMA); one more correction from a faithful quotient with a correctly rounded
+// reciprocal yields RN(a/b) (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, "division with an
+// FMA").  5 FMA-pipe instructions instead of the ~10 (one of them a MUFU) of a stand-alone IEEE division.  Valid
+// when nothing under- or overflows: the caller guards the denominator's range per cell, and quotients below 2^-90
+// (whose remainders may underflow) stay far below any confidence threshold the fast path is used with.
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
+  const float q0 = __fmul_rn(a, y);
+  const float q1 = __fmaf_rn(__fmaf_rn(-q0, b, a), y, q0);
+  return __fmaf_rn(__fmaf_rn(-q1, b, a), y, q1);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kHeatThreads, 4)
-k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, unsigned* __restrict__ hist,
-               uint2* __restrict__ cellmax, int Hc, int Wc, float conf) {
+k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __restrict__ cellmax, int Hc, int Wc,
+               int fast_div) {
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
@@ -64,34 +79,54 @@ k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, unsigned* _
   float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc) * W + 8 * wc;
   float m1 = 0.0f, m2 = 0.0f;  // largest and second largest pixel of the cell (m2 == m1 on ties)
   int arg = 0;                 // pixel index 8 * row + col of the largest
+  auto rows = [&](auto divide) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    float p[8];
+    for (int r = 0; r < 8; ++r) {
+      float p[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      p[j] = __fdiv_rn(e[8 * r + j], denom);
-      m2 = fmaxf(m2, fminf(m1, p[j]));
-      arg = p[j] > m1 ? 8 * r + j : arg;
-      m1 = fmaxf(m1, p[j]);
+      for (int j = 0; j < 8; ++j) {
+        p[j] = divide(e[8 * r + j]);
+        m2 = fmaxf(m2, fminf(m1, p[j]));
+        arg = p[j] > m1 ? 8 * r + j : arg;
+        m1 = fmaxf(m1, p[j]);
+      }
+      reinterpret_cast<float4*>(dst + (size_t)r * W)[0] = make_float4(p[0], p[1], p[2], p[3]);
+      reinterpret_cast<float4*>(dst + (size_t)r * W)[1] = make_float4(p[4], p[5], p[6], p[7]);
     }
-    reinterpret_cast<float4*>(dst + (size_t)r * W)[0] = make_float4(p[0], p[1], p[2], p[3]);
-    reinterpret_cast<float4*>(dst + (size_t)r * W)[1] = make_float4(p[4], p[5], p[6], p[7]);
-    // Sampled histogram: one pixel per (cell, row) on a diagonal -> 8 of the cell's 64 pixels.
-    // Only used to ESTIMATE the first chunk's score threshold; exactness never depends on it.
-    const int js = (r + cell) & 7;
-    float v = p[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) v = (j == js) ? p[j] : v;
-    if (v > conf) {
-      uint32_t bits = fbits(v);
-      uint32_t bin = bits >= kOneBits ? 0u : min((kOneBits - bits) >> kHistShift, (uint32_t)(kHistBins - 1));
-      atomicAdd(&hist[(size_t)b * kHistBins + bin], 1u);
-    }
+  };
+  // shared-reciprocal division when the denominator is comfortably inside the normal range (always, for finite
+  // network outputs of sane magnitude); otherwise the stand-alone IEEE division
+  if (fast_div && denom > 0x1p-60f && denom < 0x1p60f) {
+    const float rcp = __frcp_rn(denom);
+    rows([&](float a) { return div_by_rcp(a, denom, rcp); });
+  } else {
+    rows([&](float a) { return __fdiv_rn(a, denom); });
   }
   // Per-cell record for k_detect: .x = bits of the cell maximum, .y = bits of the second largest pixel with the
   // low 6 bits replaced by the argmax.  Cells that cannot hold a first-chunk candidate are skipped; cells whose
   // second pixel is below the chunk's bound yield their single candidate without touching the heatmap.
   cellmax[(size_t)b * cells + cell] = make_uint2(fbits(m1), (fbits(m2) & ~63u) | (uint32_t)arg);
+}
+
+// Self-check used by tests (spvo_debug_div_check): counts operand pairs on which the shared-reciprocal division
+// differs from __fdiv_rn.  a_bits / b_bits: n fp32 bit patterns each.
+__global__ void k_div_check(const uint32_t* __restrict__ a_bits, const uint32_t* __restrict__ b_bits, long long n,
+                            unsigned long long* __restrict__ mismatches) {
+  unsigned long long bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float(a_bits[i]), b = __uint_as_float(b_bits[i]);
+    if (!(b > 0x1p-60f && b < 0x1p60f) || !(a >= 0.0f) || !(a < 0x1p100f)) continue;  // outside the guarded domain
+    const float ref = __fdiv_rn(a, b);
+    if (ref != 0.0f && ref < 0x1p-90f) continue;  // documented: tiny quotients are not covered
+    const float got = div_by_rcp(a, b, __frcp_rn(b));
+    if (__float_as_uint(got) != __float_as_uint(ref)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+cudaError_t launch_div_check(Handle* h, const uint32_t* a_bits, const uint32_t* b_bits, long long n,
+                             unsigned long long* mismatches) {
+  k_div_check<<<h->sm_count * 8, 256, 0, h->stream>>>(a_bits, b_bits, n, mismatches);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -103,7 +138,7 @@ k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, unsigned* _
 struct DetectParams {
   const float* heat;
   const uint2* cellmax;  // [B, cells] per-cell (max bits, second-max bits | argmax) records of the heatmap
-  const unsigned* hist;
+  unsigned long long* list;  // [B, kListCap] global scratch: candidate keys of the current generation
   int H, W;
   float conf;
   int dist, border, K;
@@ -116,7 +151,7 @@ struct DetectParams {
   size_t bitmap_stride;  // words per image in `bitmap`
   unsigned* bitmap;  // [B, bitmap_stride] global scratch: pixels suppressed by earlier chunks (multi-chunk path only)
   int cap;        // key buffer capacity (power of two)
-  int target;     // candidates wanted in the first chunk
+  int target;     // cells (generation) / candidates (first chunk) wanted
 };
 
 constexpr int kDetectThreads = 512;
@@ -173,99 +208,34 @@ __device__ __forceinline__ void scan_heat(const float* __restrict__ heat, int H,
   }
 }
 
-// Collect every key in [lo, hi) into keys[] (first `cap` only); returns the total count.
-__device__ int collect_keys(const float* heat, int H, int W, uint32_t conf_bits, u64 lo, u64 hi, u64* keys,
-                            int cap, int* s_count) {
-  if (threadIdx.x == 0) *s_count = 0;
-  __syncthreads();
-  const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
-  const int lane = threadIdx.x & 31;
-  scan_heat(
-      heat, H, W, [&](uint32_t b) { return b > conf_bits && b >= lo_b && b <= hi_b && b < kInfBits; },
-      [&](bool s, uint32_t b, int x, int y) {
-        u64 key = make_key(b, x, y, H);
-        s = s && key >= lo && key < hi;
-        unsigned m = __ballot_sync(0xffffffffu, s);
-        if (m) {
-          int leader = __ffs(m) - 1, basei = 0;
-          if (lane == leader) basei = atomicAdd(s_count, __popc(m));
-          basei = __shfl_sync(0xffffffffu, basei, leader);
-          if (s) {
-            int slot = basei + __popc(m & ((1u << lane) - 1u));
-            if (slot < cap) keys[slot] = key;
-          }
-        }
-      });
-  __syncthreads();
-  return *s_count;
+// Score bin of a heat value: bin(v) = (bits(1.0f) - bits(v)) >> 14, clamped to [0, 4095]; bin 0 holds the highest
+// scores.  Used only to SIZE candidate chunks -- exactness never depends on it.
+__device__ __forceinline__ int score_bin(uint32_t bits) {
+  return bits >= kOneBits ? 0 : (int)min((kOneBits - bits) >> kHistShift, (uint32_t)(kHistBins - 1));
 }
 
-// First-chunk collection through the per-cell maxima: only cells whose maximum can reach the chunk's
-// lower bound are fetched (8 rows x 32 B each), instead of streaming the whole heatmap.  Returns the
-// number of keys >= lo (first `cap` stored), or -1 if more than `list_cap` cells qualify (caller then
-// falls back to the full scan).  hi is unbounded here.
-__device__ int collect_keys_cells(const float* __restrict__ heat, const uint2* __restrict__ cellmax, int H, int W,
-                                  uint32_t conf_bits, u64 lo, u64* keys, int cap, uint16_t* cell_list, int list_cap,
-                                  int* s_count, int* s_ncell) {
-  const int Wc = W >> 3, cells = (H >> 3) * Wc;
+// Candidate list of one image in global memory (L2-resident): every candidate key in [lo, hi), gathered ONCE through
+// the per-cell records, plus an exact histogram of their score bins in shared memory.  The chunks of the greedy walk
+// are then cut from this list (one coalesced pass over <= kListCap keys per chunk) instead of re-scanning the heatmap.
+//   * a cell whose maximum is below lo holds nothing;
+//   * a cell whose maximum lies in [lo, hi) and whose second largest pixel is below lo yields its single candidate
+//     straight from the record;
+//   * every other contributing cell (second largest pixel >= lo) is fetched (8 rows x 32 B) and filtered.
+// (second | 63) bounds the second largest pixel from above.  Returns the number of keys in [lo, hi) (the first
+// `list_cap` are stored); bins[] is incremented for every one of them.
+constexpr int kListCap = 16384;
+
+__device__ void fetch_listed_cells(const float* __restrict__ heat, int H, int W, uint32_t conf_bits, u64 lo, u64 hi,
+                                   const uint16_t* cell_list, int ncell, u64* __restrict__ list, int list_cap,
+                                   unsigned* bins, int* s_count) {
+  const int Wc = W >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    *s_count = 0;
-    *s_ncell = 0;
-  }
-  __syncthreads();
-  const uint32_t lo_b = (uint32_t)(lo >> 32);
-  constexpr int kPU = 4;  // cell records in flight per thread (the loop is latency-bound: one CTA per image)
-  for (int c0 = 0; c0 < cells; c0 += kPU * kDetectThreads) {
-    uint2 rec[kPU];
-#pragma unroll
-    for (int u = 0; u < kPU; ++u) {
-      const int c = c0 + u * kDetectThreads + threadIdx.x;
-      rec[u] = c < cells ? __ldg(cellmax + c) : make_uint2(0u, 0u);
-    }
-#pragma unroll
-    for (int u = 0; u < kPU; ++u) {
-      const int c = c0 + u * kDetectThreads + threadIdx.x;
-      const uint32_t mb = rec[u].x;
-      const bool q = c < cells && mb > conf_bits && mb >= lo_b;
-      // (second | 63) bounds the second largest pixel from above: below the chunk's bound (or the confidence
-      // threshold) means the maximum is the cell's ONLY candidate, and its position is in the record
-      const uint32_t sb = rec[u].y | 63u;
-      const bool multi = q && sb > conf_bits && sb >= lo_b;
-      bool single = q && !multi;
-      u64 key = 0ull;
-      if (single) {
-        const int hc = c / Wc, wc = c - hc * Wc, a = (int)(rec[u].y & 63u);
-        key = make_key(mb, 8 * wc + (a & 7), 8 * hc + (a >> 3), H);
-        single = key >= lo;
-      }
-      const unsigned mm = __ballot_sync(0xffffffffu, multi);
-      if (mm) {
-        int basei = 0;
-        const int leader = __ffs(mm) - 1;
-        if (lane == leader) basei = atomicAdd(s_ncell, __popc(mm));
-        basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (multi) {
-          const int slot = basei + __popc(mm & ((1u << lane) - 1u));
-          if (slot < list_cap) cell_list[slot] = (uint16_t)c;
-        }
-      }
-      const unsigned ms = __ballot_sync(0xffffffffu, single);
-      if (ms) {
-        int basei = 0;
-        const int leader = __ffs(ms) - 1;
-        if (lane == leader) basei = atomicAdd(s_count, __popc(ms));
-        basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (single) {
-          const int slot = basei + __popc(ms & ((1u << lane) - 1u));
-          if (slot < cap) keys[slot] = key;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const int ncell = *s_ncell;
-  if (ncell > list_cap) return -1;
+  const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
+  // candidate scores: above conf, finite, and inside [lo_b, hi_b]; scores EQUAL to lo_b / hi_b need the full key
+  const uint32_t lo_cmp = max(conf_bits + 1u, lo_b), hi_cmp = min(hi_b, kInfBits - 1u);
+  const uint32_t span = hi_cmp >= lo_cmp ? hi_cmp - lo_cmp : 0u;
+  if (hi_cmp < lo_cmp) return;
+  const bool lo_edge = (uint32_t)lo != 0u, hi_edge = hi_b < kInfBits;  // the boundary cuts through a score value
   // half a warp per cell: lane l16 reads row l16/2, float4 l16&1 of the cell's 8x8 block
   const int l16 = lane & 15, half = lane >> 4, row = l16 >> 1, part = l16 & 1;
   constexpr int kCU = 4;  // cells (16-byte loads) in flight per thread
@@ -288,19 +258,29 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const uint2* _
         v[u] = __ldg(reinterpret_cast<const float4*>(heat + (size_t)cy[u] * W + cx[u]));
       }
     }
-    // Hits are rare (about one pixel per fetched cell), so each thread first marks its hits in a 32-bit mask
-    // (2-3 instructions per pixel), the warp reserves its key slots with ONE scan + ONE shared atomic, and only
-    // then are the keys built and stored (predicated, in pixel order).
+    // Hits are rare (a few pixels per fetched cell).  Pass 1 marks pixels whose SCORE lies in the range with one
+    // subtract + one unsigned compare per pixel; pass 2 (lanes with marks only) builds the keys and settles pixels whose
+    // score equals a boundary score by the full key; then the warp reserves its key slots with ONE scan + ONE atomic.
     uint32_t mask = 0u;
 #pragma unroll
     for (int u = 0; u < kCU; ++u) {
       const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t bts = fbits(pv[e]);
-        bool s = ok[u] && bts > conf_bits && bts >= lo_b && bts < kInfBits;
-        if (s && bts == lo_b) s = make_key(bts, cx[u] + e, cy[u], H) >= lo;  // boundary score: full key comparison
-        mask |= (s ? 1u : 0u) << (4 * u + e);
+      for (int e = 0; e < 4; ++e)
+        if (fbits(pv[e]) - lo_cmp <= span) mask |= 1u << (4 * u + e);  // padding loads are 0.0f: below lo_cmp
+    }
+    if (mask && (lo_edge | hi_edge)) {  // some score bits coincide with a range boundary: compare full keys
+#pragma unroll
+      for (int u = 0; u < kCU; ++u) {
+        const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t bts = fbits(pv[e]);
+          if ((mask >> (4 * u + e) & 1u) && (bts == lo_b || bts == hi_b)) {
+            const u64 key = make_key(bts, cx[u] + e, cy[u], H);
+            if (!(key >= lo && key < hi)) mask &= ~(1u << (4 * u + e));
+          }
+        }
       }
     }
     const int cnt = __popc(mask);
@@ -321,15 +301,161 @@ __device__ int collect_keys_cells(const float* __restrict__ heat, const uint2* _
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (mask & (1u << (4 * u + e))) {
-            if (slot < cap) keys[slot] = make_key(fbits(pv[e]), cx[u] + e, cy[u], H);
+            const uint32_t bts = fbits(pv[e]);
+            const u64 key = make_key(bts, cx[u] + e, cy[u], H);
+            if (slot < list_cap) list[slot] = key;
+            atomicAdd(&bins[score_bin(bts)], 1u);
             ++slot;
           }
         }
       }
     }
   }
+}
+
+__device__ int collect_to_list(const float* __restrict__ heat, const uint2* __restrict__ cellmax, int H, int W,
+                               uint32_t conf_bits, u64 lo, u64 hi, u64* __restrict__ list, int list_cap,
+                               unsigned* bins, uint16_t* cell_list, int cl_cap, int* s_count, int* s_ncell) {
+  const int Wc = W >> 3, cells = (H >> 3) * Wc;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    *s_count = 0;
+    *s_ncell = 0;
+  }
+  __syncthreads();
+  const uint32_t lo_b = (uint32_t)(lo >> 32);
+  constexpr int kPU = 4;  // cell records in flight per thread
+  for (int c0 = 0; c0 < cells; c0 += kPU * kDetectThreads) {
+    uint2 rec[kPU];
+#pragma unroll
+    for (int u = 0; u < kPU; ++u) {
+      const int c = c0 + u * kDetectThreads + threadIdx.x;
+      rec[u] = c < cells ? __ldg(cellmax + c) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kPU; ++u) {
+      const int c = c0 + u * kDetectThreads + threadIdx.x;
+      const uint32_t mb = rec[u].x;
+      const bool q = c < cells && mb > conf_bits && mb >= lo_b && mb < kInfBits;
+      const uint32_t sb = rec[u].y | 63u;
+      const bool multi = q && sb > conf_bits && sb >= lo_b;
+      bool single = q && !multi;
+      u64 key = 0ull;
+      if (single) {
+        const int hc = c / Wc, wc = c - hc * Wc, a = (int)(rec[u].y & 63u);
+        key = make_key(mb, 8 * wc + (a & 7), 8 * hc + (a >> 3), H);
+        single = key >= lo && key < hi;
+      }
+      const unsigned mm = __ballot_sync(0xffffffffu, multi);
+      if (mm) {
+        int basei = 0;
+        const int leader = __ffs(mm) - 1;
+        if (lane == leader) basei = atomicAdd(s_ncell, __popc(mm));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (multi) cell_list[basei + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)c;  // never past cl_cap: flushed below
+      }
+      const unsigned ms = __ballot_sync(0xffffffffu, single);
+      if (ms) {
+        int basei = 0;
+        const int leader = __ffs(ms) - 1;
+        if (lane == leader) basei = atomicAdd(s_count, __popc(ms));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (single) {
+          const int slot = basei + __popc(ms & ((1u << lane) - 1u));
+          if (slot < list_cap) list[slot] = key;
+          atomicAdd(&bins[score_bin(mb)], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    // fetch the listed cells before the list can overflow (a block of records adds at most kPU * threads cells)
+    if (*s_ncell + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
+      const int ncell = *s_ncell;
+      fetch_listed_cells(heat, H, W, conf_bits, lo, hi, cell_list, ncell, list, list_cap, bins, s_count);
+      __syncthreads();
+      if (threadIdx.x == 0) *s_ncell = 0;
+      __syncthreads();
+    }
+  }
+  return *s_count;
+}
+
+// Keys of list[0 .. n_list) inside [lo, hi) -> keys[] (first `cap` stored); returns their number.
+__device__ int select_from_list(const u64* __restrict__ list, int n_list, u64 lo, u64 hi, u64* keys, int cap,
+                                int* s_count) {
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr int kLU = 4;  // list loads in flight per thread (the list lives in L2)
+  for (int i0 = 0; i0 < n_list; i0 += kLU * kDetectThreads) {
+    u64 kk[kLU];
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      const int i = i0 + u * kDetectThreads + threadIdx.x;
+      kk[u] = i < n_list ? list[i] : 0ull;  // plain load: the list was written by this CTA
+    }
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      const u64 key = kk[u];
+      const bool s = key >= lo && key < hi && key != 0ull;
+      const unsigned m = __ballot_sync(0xffffffffu, s);
+      if (m) {
+        int basei = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) basei = atomicAdd(s_count, __popc(m));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (s) {
+          const int slot = basei + __popc(m & ((1u << lane) - 1u));
+          if (slot < cap) keys[slot] = key;
+        }
+      }
+    }
+  }
   __syncthreads();
   return *s_count;
+}
+
+// Exact radix select over the candidate list: the m-th largest key among list keys < hi, or `floor_key` when fewer
+// than m remain.  8 passes of 8 bits over <= kListCap keys (only when one score bin alone overflows a chunk).
+__device__ u64 radix_select_list(const u64* __restrict__ list, int n_list, u64 hi, int m, u64 floor_key,
+                                 unsigned* s_hist, u64* s_prefix, int* s_want) {
+  if (threadIdx.x == 0) {
+    *s_prefix = 0;
+    *s_want = m;
+  }
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += kDetectThreads) s_hist[i] = 0;
+    __syncthreads();
+    const u64 prefix = *s_prefix;
+    for (int i = threadIdx.x; i < n_list; i += kDetectThreads) {
+      const u64 key = list[i];
+      if (key < hi && (pass == 0 || (key >> (shift + 8)) == prefix)) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int want = *s_want, cum = 0, d = 255;
+      bool found = false;
+      for (; d >= 0; --d) {
+        const int c = (int)s_hist[d];
+        if (cum + c >= want) {
+          found = true;
+          break;
+        }
+        cum += c;
+      }
+      if (!found) {
+        *s_want = -1;
+      } else {
+        *s_want = want - cum;
+        *s_prefix = (prefix << 8) | (u64)d;
+      }
+    }
+    __syncthreads();
+    if (*s_want < 0) return floor_key;
+  }
+  const u64 thr = *s_prefix;
+  return thr < floor_key ? floor_key : thr;
 }
 
 // Exact radix select: returns the m-th largest key among candidate keys < hi (unique keys), or
@@ -448,49 +574,144 @@ __device__ void bitonic_sort_desc(u64* keys, int n_pad) {
   }
 }
 
-// Smallest histogram bin index B >= bin_from such that 8 * (count of bins bin_from .. B) >= want_pixels
-// (the histogram holds one of every 8 pixels); kHistBins-1 if the whole tail is not enough.  Block-wide;
-// an ESTIMATE used to size a chunk -- exactness never depends on it.
-__device__ int hist_pick_bin(const unsigned* __restrict__ hist, int bin_from, int want_pixels, unsigned* s_warp_tot,
-                             int* s_bin) {
+// Chunk of the walk, SORTED, by a bucket sort on the score bins: the exact per-bin counts of the list (bins[]) give
+// every bin of the chunk its slice of keys[] (block-wide exclusive scan), the list keys in [lo, hi) are scattered into
+// their slices (bin 0 = highest scores first), and each slice -- a handful of keys -- is finished by an insertion
+// sort on the full 64-bit key.  Replaces a 2048-4096-key bitonic sort (66-78 compare-exchange stages) by three short
+// passes.  Returns the number of keys, or -1 when some bin holds more than kMaxBucket keys (massive ties): the caller
+// then uses the generic select + bitonic path.  bstart: kHistBins + 1 ints of scratch.
+constexpr int kMaxBucket = 48;
+constexpr int kBucketMax = 4096;  // largest chunk the bucket sort takes (8 keys per thread in registers)
+__device__ int bucket_sort_chunk(const u64* __restrict__ list, int n_list, u64 lo, u64 hi, int bfrom, int bto,
+                                 const unsigned* bins, int* bstart, u64* keys, int cap, unsigned* s_warp_tot,
+                                 int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int per = kHistBins / kDetectThreads;
-  if (tid == 0) *s_bin = kHistBins - 1;
+  if (tid == 0) *s_flag = 0;
+  unsigned loc[per], sum = 0, mx = 0;
+#pragma unroll
+  for (int i = 0; i < per; ++i) {
+    const int bin = tid * per + i;
+    loc[i] = (bin >= bfrom && bin <= bto) ? bins[bin] : 0u;
+    sum += loc[i];
+    mx = max(mx, loc[i]);
+  }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp_tot[warp] = inc;
+  if (mx > (unsigned)kMaxBucket) *s_flag = 1;
+  __syncthreads();
+  unsigned off = 0, total = 0;
+  for (int w = 0; w < kDetectThreads / 32; ++w) {
+    if (w < warp) off += s_warp_tot[w];
+    total += s_warp_tot[w];
+  }
+  if (*s_flag || total > (unsigned)min(cap, kBucketMax)) return -1;
+  unsigned run = off + inc - sum;
+#pragma unroll
+  for (int i = 0; i < per; ++i) {
+    bstart[tid * per + i] = (int)run;  // becomes the slice's END after the scatter
+    run += loc[i];
+  }
+  __syncthreads();
+  constexpr int kLU = 8;  // list loads in flight per thread (the list lives in L2)
+  for (int i0 = 0; i0 < n_list; i0 += kLU * kDetectThreads) {
+    u64 kk[kLU];
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      const int i = i0 + u * kDetectThreads + tid;
+      kk[u] = i < n_list ? list[i] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      const u64 key = kk[u];
+      if (key >= lo && key < hi && key != 0ull) keys[atomicAdd(&bstart[score_bin((uint32_t)(key >> 32))], 1)] = key;
+    }
+  }
+  __syncthreads();
+  // finish every slice by RANKING: one thread per key counts the keys of its slice that are larger (slices hold a
+  // handful of keys; a thread-per-slice insertion sort left the block waiting for the fullest slice)
+  constexpr int kKU = kBucketMax / kDetectThreads;  // keys per thread
+  u64 mine[kKU];
+  uint16_t dest[kKU];
+#pragma unroll
+  for (int u = 0; u < kKU; ++u) {
+    const int i = u * kDetectThreads + tid;
+    mine[u] = 0ull;
+    dest[u] = 0;
+    if (i < (int)total) {
+      const u64 key = keys[i];
+      const int bin = score_bin((uint32_t)(key >> 32));
+      const int end = bstart[bin], start = bin == bfrom ? 0 : bstart[bin - 1];
+      int rank = 0;
+      for (int j = start; j < end; ++j) rank += keys[j] > key ? 1 : 0;
+      mine[u] = key;
+      dest[u] = (uint16_t)(start + rank);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kKU; ++u)
+    if (u * kDetectThreads + tid < (int)total) keys[dest[u]] = mine[u];
+  __syncthreads();
+  return (int)total;
+}
+
+// Block-wide search in a 4096-bin histogram held in SHARED memory: the smallest bin B >= bin_from whose running count
+// from bin_from reaches `want` (kHistBins-1 when the whole tail holds less).  s_res[0] = B, s_res[1] = count of
+// bins bin_from .. B, s_res[2] = count of bins bin_from .. B-1.
+__device__ void pick_bin(const unsigned* bins, int bin_from, int want, unsigned* s_warp_tot, int* s_res) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int per = kHistBins / kDetectThreads;
   unsigned loc[per], sum = 0;
 #pragma unroll
   for (int i = 0; i < per; ++i) {
     const int bin = tid * per + i;
-    loc[i] = bin >= bin_from ? hist[bin] : 0u;
+    loc[i] = bin >= bin_from ? bins[bin] : 0u;
     sum += loc[i];
   }
   unsigned inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += v;
   }
   __syncthreads();
   if (lane == 31) s_warp_tot[warp] = inc;
   __syncthreads();
-  unsigned off = 0;
-  for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+  unsigned off = 0, total = 0;
+  for (int w = 0; w < kDetectThreads / 32; ++w) {
+    if (w < warp) off += s_warp_tot[w];
+    total += s_warp_tot[w];
+  }
   const unsigned excl = off + inc - sum;
-  const unsigned want = (unsigned)((want_pixels + 7) / 8);
-  if (excl < want && excl + sum >= want) {
+  const unsigned uwant = (unsigned)max(want, 1);
+  if (tid == 0 && total < uwant) {  // the tail holds less than wanted: take all of it
+    s_res[0] = kHistBins - 1;
+    s_res[1] = (int)total;
+    s_res[2] = (int)total;
+  }
+  if (excl < uwant && excl + sum >= uwant) {
     unsigned c = excl;
     for (int i = 0; i < per; ++i) {
-      c += loc[i];
-      if (c >= want) {
-        *s_bin = tid * per + i;
+      if (c + loc[i] >= uwant) {
+        s_res[0] = tid * per + i;
+        s_res[1] = (int)(c + loc[i]);
+        s_res[2] = (int)c;
         break;
       }
+      c += loc[i];
     }
   }
   __syncthreads();
-  return *s_bin;
 }
 
-// lower key bound (inclusive) of "all pixels whose histogram bin is <= bin"
+// lower key bound (inclusive) of "all pixels whose score bin is <= bin"
 __device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
   if (bin >= kHistBins - 1) return floor_key;
   const uint32_t tb = kOneBits - ((uint32_t)(bin + 1) << kHistShift);  // bin(v) <= bin  <=>  bits > tb
@@ -516,61 +737,135 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   const int Hc = H >> 3, Wc = W >> 3, cells = Hc * Wc;
   u64* keys = reinterpret_cast<u64*>(smem_raw);                  // [cap]   sorted candidate keys of the chunk
   u64* emit = keys + cap;                                        // [K]     emitted keypoints (score | y<<16 | x)
-  int* head = reinterpret_cast<int*>(emit + K);                  // [cells] spatial hash: first candidate of a cell
+  int* head = reinterpret_cast<int*>(emit + K);                  // [cells + 1] spatial hash: start of each cell's run in next[]
   // pixels suppressed by EARLIER chunks live in a global-memory bitmap that only the multi-chunk path touches
   // (zeroed lazily), which keeps the CTA at ~85 KB of shared memory: two images per SM
   unsigned* bitmap = p.bitmap + (size_t)b * p.bitmap_stride;
   bool have_bitmap = false;
-  uint16_t* next = reinterpret_cast<uint16_t*>(head + cells);    // [cap]
+  uint16_t* next = reinterpret_cast<uint16_t*>(head + max(cells + 2, kHistBins + 2)); // [cap]   candidates grouped by cell (also the cell list of the gather)
   uint8_t* state = reinterpret_cast<uint8_t*>(next + cap);       // [2*cap] (second half: Jacobi double buffer)
   unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
-  __shared__ int s_count, s_want, s_bin, s_emitted;
+  unsigned* bins = reinterpret_cast<unsigned*>(state + 2 * cap); // [kHistBins] score-bin histogram (chunk sizing)
+  u64* list = p.list + (size_t)b * kListCap;                     // this image's candidate list (global, L2-resident)
+  __shared__ int s_count, s_want, s_emitted;
+  __shared__ int s_res[3];
   __shared__ u64 s_prefix;
   __shared__ unsigned s_warp_tot[kDetectThreads / 32];
 
   const float* heat = p.heat + (size_t)b * H * W;
+  const uint2* cellmax = p.cellmax + (size_t)b * cells;
   const uint32_t conf_bits = fbits(fmaxf(p.conf, 0.0f));
   const u64 floor_key = ((u64)conf_bits + 1ull) << 32;  // smallest possible candidate key (score > conf)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
     s_emitted = 0;
-    s_bin = kHistBins - 1;
     if (p.opmax_zero) p.opmax_zero[b] = 0u;  // k_desc_normalize takes an atomicMax into it (saves a memset node)
   }
 
-  // ---- first-chunk threshold from the sampled histogram (estimate only) ------------------------
-  const unsigned* hist = p.hist + (size_t)b * kHistBins;
-  int cur_bin = hist_pick_bin(hist, 0, p.target, s_warp_tot, &s_bin);
-  u64 hi = ~0ull;
-  u64 lo = bin_to_lo_key(cur_bin, floor_key);
-  __syncthreads();
-
+  // Candidates are consumed in descending key order.  A GENERATION gathers every candidate of a key range
+  // [lo_pre, hi_pre) ONCE into the image's global list (through the per-cell records: only contributing cells are
+  // touched), with an exact score-bin histogram; the CHUNKS of the greedy walk are then cut from the list at bin
+  // boundaries.  Normally there is one generation and (on independent-pixel heatmaps) one chunk; sparse, clustered
+  // heatmaps of a real network need several chunks because most of their candidates are suppressed.  All sizing is
+  // heuristic; overflow is detected exactly and repaired, so the result always equals full sort + sequential walk.
   bool slow = false;
-  // ---- chunk loop: consume candidates in descending key order ----------------------------------
-  bool first = true;
+  u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
+  int walked = 0;
   while (true) {
-    int n = -1;
-    if (first && p.cellmax)  // first chunk (hi unbounded): fetch only the cells that can contribute
-      n = collect_keys_cells(heat, p.cellmax + (size_t)b * cells, H, W, conf_bits, lo, keys, cap, next, cap, &s_count,
-                             &s_want);
-    first = false;
-    if (n < 0) n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
-    if (n > cap) {  // estimate too generous (or heavy ties): shrink the chunk exactly
-      slow = true;
-      __syncthreads();
-      lo = radix_select(heat, H, W, conf_bits, hi, cap, floor_key, s_hist, &s_prefix, &s_want);
-      __syncthreads();
-      n = collect_keys(heat, H, W, conf_bits, lo, hi, keys, cap, &s_count);
-    }
-    int n_pad = 32;
-    while (n_pad < n) n_pad <<= 1;
-    for (int i = n + tid; i < n_pad; i += kDetectThreads) keys[i] = 0ull;
-    for (int i = tid; i < cells; i += kDetectThreads) head[i] = -1;
+    // ---- G1: range of the generation from the histogram of cell MAXIMA (an estimate) ----------------
+    for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
     __syncthreads();
-    bitonic_sort_desc(keys, n_pad);
+    {
+      const uint32_t hi_b = (uint32_t)(hi_pre >> 32);
+      for (int c = tid; c < cells; c += kDetectThreads) {
+        const uint32_t mb = __ldg(&cellmax[c].x);
+        if (mb > conf_bits && mb < kInfBits && mb <= hi_b) atomicAdd(&bins[score_bin(mb)], 1u);
+      }
+    }
+    __syncthreads();
+    pick_bin(bins, 0, p.target, s_warp_tot, s_res);
+    u64 lo_pre = bin_to_lo_key(s_res[0], floor_key);
+    const int gen_cells = max(s_res[1], 1);  // cells whose maximum lies in the generation's range
+    if (lo_pre >= hi_pre) lo_pre = floor_key;
+    __syncthreads();
+    // ---- G2: gather [lo_pre, hi_pre) into the list; exact bins --------------------------------------
+    int n_list;
+    while (true) {
+      for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
+      __syncthreads();
+      n_list = collect_to_list(heat, cellmax, H, W, conf_bits, lo_pre, hi_pre, list, kListCap, bins, next, cap, &s_count,
+                               &s_want);
+      __syncthreads();
+      if (n_list <= kListCap) break;
+      slow = true;  // more candidates than the list holds: raise the lower bound exactly and gather again
+      pick_bin(bins, 0, kListCap * 3 / 4, s_warp_tot, s_res);
+      u64 lo2 = s_res[1] <= kListCap ? bin_to_lo_key(s_res[0], floor_key)
+                                     : (s_res[2] > 0 ? bin_to_lo_key(s_res[0] - 1, floor_key) : 0ull);
+      __syncthreads();
+      if (lo2 <= lo_pre) {  // one score bin alone overflows the list (massive ties): exact select on the heatmap
+        lo2 = radix_select(heat, H, W, conf_bits, hi_pre, kListCap * 3 / 4, floor_key, s_hist, &s_prefix, &s_want);
+        __syncthreads();
+      }
+      lo_pre = lo2;
+    }
+    // ---- G3: chunks of the walk ---------------------------------------------------------------------
+    u64 hi = hi_pre;
+    // Clustered heatmaps (a real network: ~7 candidates per contributing cell, most of them suppressed by their
+    // blob's peak) need a walk several times longer than K: size the first chunk by the observed candidates per cell
+    // instead of discovering that one small chunk at a time.  Independent pixels (~1 per cell) keep the small chunk.
+    int bfrom = 0;
+    int chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512),
+                                max((long long)p.target, (long long)K * n_list * 6 / (10LL * gen_cells) + 256));
+    bool done = false;
+    bool whole = n_list <= min(cap * 3 / 4, p.target + p.target / 2);  // small list: the first chunk takes all of it
+    bool stale_bins = false;  // a bin was cut inside (exact select): its count no longer matches the remaining keys
+    while (true) {
+      int bto = kHistBins - 1;
+      u64 lo;
+      if (whole) {
+        lo = lo_pre;
+      } else {
+        pick_bin(bins, bfrom, chunk_target, s_warp_tot, s_res);
+        bto = s_res[0];
+      }
+      if (whole) {
+      } else if (s_res[1] <= cap) {
+        lo = bin_to_lo_key(bto, floor_key);
+      } else if (s_res[2] > 0) {
+        bto -= 1;
+        lo = bin_to_lo_key(bto, floor_key);
+      } else {  // one score bin alone overflows the chunk buffer: cut it exactly (its count stays stale; the
+                // selection below is exact, so later chunks can only be smaller than estimated)
+        __syncthreads();
+        lo = radix_select_list(list, n_list, hi, cap * 3 / 4, lo_pre, s_hist, &s_prefix, &s_want);
+        bto -= 1;
+        stale_bins = true;
+      }
+      if (lo < lo_pre) lo = lo_pre;
+      __syncthreads();
+      // sorted chunk: bucket sort on the exact bins, or (stale bin counts after an exact cut / massive ties) the
+      // generic selection + bitonic sort
+      int n = -1;
+      if (!stale_bins)
+        n = bucket_sort_chunk(list, n_list, lo, hi, bfrom, min(bto, kHistBins - 1), bins, head, keys, cap, s_warp_tot, &s_want);
+      if (n < 0) {
+        __syncthreads();
+        n = select_from_list(list, n_list, lo, hi, keys, cap, &s_count);
+        int n_pad = 32;
+        while (n_pad < n) n_pad <<= 1;
+        for (int i = n + tid; i < n_pad; i += kDetectThreads) keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(keys, n_pad);
+      }
+      whole = false;
+      walked += n;
+    for (int i = tid; i <= cells; i += kDetectThreads) head[i] = 0;
+    __syncthreads();
 
     // ---- A: unpack positions, initial states, spatial hash ---------------------------------------
+    // The hash is a counting sort of the candidates by 8x8-pixel cell: head[c] .. head[c+1] delimit the cell's
+    // candidates in next[] (contiguous, so a neighbourhood scan issues independent loads instead of chasing links).
     for (int i = tid; i < n; i += kDetectThreads) {
       const u64 key = keys[i];
       const uint32_t pos = 0xFFFFFFFFu - (uint32_t)key;
@@ -579,9 +874,41 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       const bool sup = have_bitmap && ((bitmap[y * ww + (x >> 5)] >> (x & 31)) & 1u);
       state[i] = sup ? ST_SUPP : ST_UNDEC;
       // d == 0: a point only suppresses its own pixel, nothing interacts
-      if (!sup && d > 0) next[i] = (uint16_t)atomicExch(&head[(y >> 3) * Wc + (x >> 3)], i);
+      if (!sup && d > 0) atomicAdd(&head[(y >> 3) * Wc + (x >> 3)], 1);
     }
     __syncthreads();
+    if (d > 0) {
+      // exclusive scan of the per-cell counts (each thread owns a run of consecutive cells)
+      const int per = (cells + kDetectThreads - 1) / kDetectThreads;
+      const int c0 = min(tid * per, cells), c1 = min(c0 + per, cells);
+      int sum = 0;
+      for (int c = c0; c < c1; ++c) sum += head[c];
+      int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) s_warp_tot[warp] = (unsigned)inc;
+      __syncthreads();
+      int off = 0;
+      for (int w = 0; w < warp; ++w) off += (int)s_warp_tot[w];
+      int run = off + inc - sum;
+      for (int c = c0; c < c1; ++c) {  // head[c] = start | (count << 16): the count is consumed by the scatter below
+        const int cnt = head[c];
+        head[c] = run | (cnt << 16);
+        run += cnt;
+      }
+      if (tid == kDetectThreads - 1) head[cells] = run;
+      __syncthreads();
+      for (int i = tid; i < n; i += kDetectThreads) {
+        if (state[i] != ST_UNDEC) continue;
+        const uint32_t xy = (uint32_t)keys[i];
+        const int old = atomicSub(&head[(int)(xy >> 19) * Wc + (int)((xy & 0xFFFF) >> 3)], 1 << 16);
+        next[(old & 0xFFFF) + (old >> 16) - 1] = (uint16_t)i;
+      }
+      __syncthreads();
+    }
 
     // ---- B: fixed-point rounds ---------------------------------------------------------------------
     if (d == 0) {
@@ -604,19 +931,22 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
             const int cx0 = max(x - d, 0) >> 3, cx1 = min(x + d, W - 1) >> 3;
             const int cy0 = max(y - d, 0) >> 3, cy1 = min(y + d, H - 1) >> 3;
             bool kept = false, undec = false;
-            for (int cy = cy0; cy <= cy1; ++cy)
-              for (int cx = cx0; cx <= cx1; ++cx)
-                for (int q = head[cy * Wc + cx]; q >= 0 && q != kNil; q = next[q]) {
-                  if (q < i) {
-                    const uint32_t qxy = (uint32_t)keys[q];
-                    const int qx = qxy & 0xFFFF, qy = qxy >> 16;
-                    if (abs(qx - x) <= d && abs(qy - y) <= d) {
-                      const uint8_t sq = st_in[q];
-                      kept |= sq == ST_KEPT;
-                      undec |= sq == ST_UNDEC;
-                    }
+            for (int cy = cy0; cy <= cy1 && !kept; ++cy) {
+              // the cells cx0 .. cx1 of one cell row are adjacent in the counting sort: one contiguous range
+              const int k1 = head[cy * Wc + cx1 + 1];
+              for (int k = head[cy * Wc + cx0]; k < k1; ++k) {
+                const int q = next[k];
+                if (q < i) {
+                  const uint32_t qxy = (uint32_t)keys[q];
+                  const int qx = qxy & 0xFFFF, qy = qxy >> 16;
+                  if (abs(qx - x) <= d && abs(qy - y) <= d) {
+                    const uint8_t sq = st_in[q];
+                    kept |= sq == ST_KEPT;
+                    undec |= sq == ST_UNDEC;
                   }
                 }
+              }
+            }
             if (kept) so = ST_SUPP;
             else if (!undec) so = ST_KEPT;
             else ++undecided;
@@ -672,34 +1002,43 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       if (tid == 0) s_emitted = min(K, s_emitted + total);
       __syncthreads();
     }
-    if (s_emitted >= K || lo <= floor_key) break;
+      const bool list_done = lo <= lo_pre;  // this chunk took the rest of the generation's list
+      if (s_emitted >= K || (list_done && lo_pre <= floor_key)) {
+        done = true;
+        break;
+      }
 
-    // ---- D: more candidates are needed: record this chunk's boxes, take the next `cap` keys --------
-    slow = true;
-    if (!have_bitmap) {
-      for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
-      have_bitmap = true;
+      // ---- D: more candidates are needed: record this chunk's boxes for the candidates still to come ----
+      slow = true;
+      if (!have_bitmap) {
+        for (int i = tid; i < H * ww; i += kDetectThreads) bitmap[i] = 0u;
+        have_bitmap = true;
+        __syncthreads();
+      }
+      for (int i = tid; i < n; i += kDetectThreads) {
+        if (state[i] != ST_KEPT) continue;
+        const uint32_t xy = (uint32_t)keys[i];
+        const int xj = xy & 0xFFFF, yj = xy >> 16;
+        const int x0 = max(xj - d, 0), x1 = min(xj + d, W - 1);
+        for (int yy = max(yj - d, 0); yy <= min(yj + d, H - 1); ++yy)
+          for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+            const int lo_b = max(x0 - (w << 5), 0), hi_b = min(x1 - (w << 5), 31);
+            atomicOr(&bitmap[yy * ww + w], (0xffffffffu >> (31 - hi_b)) & (0xffffffffu << lo_b));
+          }
+      }
+      __syncthreads();
+      hi = lo;
+      if (list_done) break;  // next generation: gather the candidates below lo_pre
+      bfrom = bto + 1;
+      // size the next chunk from what the walk has yielded so far: (K - emitted) more keypoints at the observed
+      // emission rate, with a margin; bounded by the buffer
+      const int em = max(s_emitted, 1);
+      const long long need = (long long)(K - s_emitted) * walked / em;
+      chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512), max(512LL, need + need / 4 + 128));
       __syncthreads();
     }
-    for (int i = tid; i < n; i += kDetectThreads) {
-      if (state[i] != ST_KEPT) continue;
-      const uint32_t xy = (uint32_t)keys[i];
-      const int xj = xy & 0xFFFF, yj = xy >> 16;
-      const int x0 = max(xj - d, 0), x1 = min(xj + d, W - 1);
-      for (int yy = max(yj - d, 0); yy <= min(yj + d, H - 1); ++yy)
-        for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
-          const int lo_b = max(x0 - (w << 5), 0), hi_b = min(x1 - (w << 5), 31);
-          atomicOr(&bitmap[yy * ww + w], (0xffffffffu >> (31 - hi_b)) & (0xffffffffu << lo_b));
-        }
-    }
-    __syncthreads();
-    hi = lo;
-    // size the next chunk from the histogram again (about 3/4 of the buffer); if the estimate overflows the
-    // buffer the loop's overflow branch shrinks it exactly with the radix select
-    cur_bin = hist_pick_bin(hist, cur_bin + 1, cap * 3 / 4, s_warp_tot, &s_bin);
-    lo = bin_to_lo_key(cur_bin, floor_key);
-    if (lo >= hi) lo = floor_key;  // cannot happen for increasing bins; keeps the loop finite regardless
-    __syncthreads();
+    if (done) break;
+    hi_pre = lo_pre;
   }
 
   // ---- outputs ---------------------------------------------------------------------------------
@@ -999,7 +1338,8 @@ static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   const int ww = (W + 31) >> 5;
   const size_t cells = (size_t)(H / 8) * (W / 8);
   (void)ww;
-  return (size_t)cap * 8 + (size_t)K * 8 + cells * 4 + (size_t)cap * 2 + (size_t)cap * 2;
+  const size_t head_ints = cells + 2 > (size_t)kHistBins + 2 ? cells + 2 : (size_t)kHistBins + 2;  // also the bucket sort's scratch
+  return (size_t)cap * 8 + (size_t)K * 8 + head_ints * 4 + (size_t)cap * 2 + (size_t)cap * 2 + (size_t)kHistBins * 4;
 }
 
 // One contiguous range of images [b0, b0 + B) on the handle's CURRENT stream (h->stream).
@@ -1018,22 +1358,24 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
   n_out += b0;
   if (scores) scores += (size_t)b0 * K;
   float* heat = h->heat + (size_t)b0 * H * W;
-  unsigned* hist = h->hist + (size_t)b0 * kHistBins;
   uint2* cellmax = h->cellmax + (size_t)b0 * cells;
-  if ((e = cudaMemsetAsync(hist, 0, (size_t)B * kHistBins * sizeof(unsigned), st)) != cudaSuccess) return e;
   dim3 g1((cells + kHeatThreads - 1) / kHeatThreads, B);
+  // quotients below 2^-90 may differ from the IEEE division in the shared-reciprocal form: harmless while they cannot
+  // be candidates (conf_thresh default 0.015); an (absurdly) small threshold takes the stand-alone division
+  const int fast_div = cfg.conf_thresh >= 1e-20f ? 1 : 0;
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
     if (in_f16)
-      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, hist, cellmax, Hc,
-                                                          Wc, cfg.conf_thresh);
+      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, cellmax, Hc, Wc,
+                                                          fast_div);
     else
-      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, hist, cellmax, Hc,
-                                                         Wc, cfg.conf_thresh);
+      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, cellmax, Hc, Wc,
+                                                         fast_div);
   }
   if (K > 0) {
     DetectParams p;
-    p.heat = heat; p.cellmax = cellmax; p.hist = hist; p.H = H; p.W = W; p.conf = cfg.conf_thresh;
+    p.heat = heat; p.cellmax = cellmax; p.list = h->cand_list + (size_t)b0 * kListCap; p.H = H; p.W = W;
+    p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
     const int per16 = (int)(16 / esz);  // one 16-byte unit of slack for the address phase, pitch in whole units
@@ -1153,5 +1495,6 @@ cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_
 }
 
 size_t decode_smem_required(int H, int W, int K) { return detect_smem_bytes(H, W, K, K <= 1536 ? 4096 : 8192); }
+size_t decode_list_bytes_per_image() { return (size_t)kListCap * sizeof(u64); }
 
 }  // namespace spvo

@@ -82,6 +82,13 @@ class Frontend:
         self._check(self._L.spvo_debug_counters(self._h, out.ctypes.data, 8))
         return out
 
+    def div_check(self, a_bits, b_bits) -> int:
+        """Mismatches between k_softmax_heat's shared-reciprocal division and the IEEE division on the given operand
+        bit patterns (CUDA int32/uint32 tensors of equal length).  Test hook; must return 0."""
+        n = C.c_longlong(0)
+        self._check(self._L.spvo_debug_div_check(self._h, _ptr(a_bits), _ptr(b_bits), a_bits.numel(), C.byref(n)))
+        return int(n.value)
+
     def profile_enable(self, on: bool = True):
         self._check(self._L.spvo_profile_enable(self._h, int(on)))
 
