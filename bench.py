@@ -448,24 +448,43 @@ def run_ours(args, rank, world, local_rank):
     out4 = fe4.alloc_stereo_out(1, K4, device=dev)
     cfg4 = dict(max_keypoints=K4, mode=S.MATCH_NN_CROSSCHECK, stereo_threshold=2.0, min_disparity=0.25)
     lat = {}
-    for name, kw in (("plain_launches", {}), ("library_graph", {"graph": True})):
-        try:
-            fe4.stereo_reset()
-            for i in range(8):
-                fe4.stereo_batch_device(s4[i % 32], d4[i % 32], 1, H4, W4, out4, **cfg4, **kw)
-            torch.cuda.synchronize()
-            n4 = 200
-            e0.record(stream)
-            for i in range(n4):
-                fe4.stereo_batch_device(s4[i % 32], d4[i % 32], 1, H4, W4, out4, **cfg4, **kw)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            lat[name + "_us_per_pair"] = 1e3 * e0.elapsed_time(e1) / n4
-        except TypeError:
-            lat[name + "_us_per_pair"] = None
+    # the network's outputs land in FIXED bindings (as a TensorRT engine's do, NN:170-176): every call is preceded by a
+    # device copy of the next frame's tensors into them (outside the timed events), so the inputs are L2-warm
+    bs4, bd4 = torch.empty_like(s4[0]), torch.empty_like(d4[0])
+    n4 = 200
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n4)]
+    for name, graph in (("plain_launches", False), ("library_graph", True)):
+        fe4.set_graph_mode(graph)
+        fe4.stereo_reset()
+        for i in range(8):
+            bs4.copy_(s4[i % 32]); bd4.copy_(d4[i % 32])
+            fe4.stereo_batch_device(bs4, bd4, 1, H4, W4, out4, **cfg4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n4):
+            bs4.copy_(s4[i % 32]); bd4.copy_(d4[i % 32])
+            evs[i][0].record(stream)
+            fe4.stereo_batch_device(bs4, bd4, 1, H4, W4, out4, **cfg4)
+            evs[i][1].record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        us = sorted(1e3 * a.elapsed_time(b_) for a, b_ in evs)
+        lat[name + "_us_per_pair"] = sum(us) / n4
+        lat[name + "_us_median"] = us[n4 // 2]
+        lat[name + "_wall_us_per_call"] = 1e6 * wall / n4
+    fe4.set_graph_mode(False)
+    # per-kernel device time of one call (events around every launch: adds gaps, so only the split is meaningful)
+    fe4.profile_enable(True)
+    fe4.profile_read()
+    for i in range(50):
+        fe4.stereo_batch_device(s4[i % 32], d4[i % 32], 1, H4, W4, out4, **cfg4)
+    prof4 = fe4.profile_read()
+    fe4.profile_enable(False)
+    lat["kernel_us"] = {k: round(1e3 * v[0] / 50, 2) for k, v in sorted(prof4.items(), key=lambda kv: -kv[1][0])}
     latency = {"workload": "640x192_K500_nn_crosscheck_one_pair_per_call", **lat,
                "roofline_us": 5.98e6 / (peaks["hbm"] * 1e9) * 1e6,
-               "timing": "200 back-to-back calls, CUDA events on the launching stream (device time per call)"}
+               "timing": "200 calls, CUDA events around each call on the launching stream (device time per call); "
+                         "wall = host loop incl. the input copy and the Python / ctypes call overhead"}
     fe4.close()
 
     if rank == 0:

@@ -214,6 +214,12 @@ typedef struct spvo_stereo_out { /* all device pointers (_device form) or all ho
 } spvo_stereo_out;
 
 int spvo_stereo_reset(spvo_handle h);
+/* Graph mode for spvo_stereo_batch_device[_f16] (off by default): the launches of a call are captured into a CUDA
+ * graph owned by the handle, once per call signature (pointers, sizes, configuration, stream, and the handle's stream
+ * state), and replayed on later calls with the same signature; a change re-captures.  Meant for the reference's
+ * real-time shape -- one stereo pair per callback with fixed engine output bindings (visual_odometry_node.cpp:150-262)
+ * -- where the dozen dependent launches of one pair are latency-, not throughput-bound.  Results are identical. */
+int spvo_set_graph_mode(spvo_handle h, int on);
 int spvo_stereo_batch_device(spvo_handle h, const float* semi, const float* desc, int F, int H, int W,
                              const spvo_stereo_cfg* cfg, const spvo_stereo_out* out);
 /* Host-pointer form: H2D of the inputs, the device pipeline, D2H of every non-NULL output, sync.

@@ -45,7 +45,7 @@ class StereoOut(C.Structure):
 SYMBOLS = [
     "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
     "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
-    "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch",
+    "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_set_graph_mode", "spvo_stereo_batch_device", "spvo_stereo_batch",
     "spvo_decode_f16", "spvo_decode_device_f16", "spvo_stereo_batch_f16", "spvo_stereo_batch_device_f16",
     "spvo_kernel_launches", "spvo_debug_counters", "spvo_debug_div_check", "spvo_profile_enable", "spvo_profile_num_kernels",
     "spvo_profile_kernel_name", "spvo_profile_read",
@@ -84,6 +84,8 @@ def load():
     L.spvo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
     L.spvo_stereo_filter_batch_device.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp, vp, cf, cf, vp]
     L.spvo_stereo_reset.argtypes = [vp]
+    L.spvo_set_graph_mode.argtypes = [vp, ci]
+    L.spvo_set_graph_mode.restype = ci
     ster = [vp, vp, vp, ci, ci, ci, C.POINTER(StereoCfg), C.POINTER(StereoOut)]
     L.spvo_stereo_batch_device.argtypes = ster
     L.spvo_stereo_batch.argtypes = ster

@@ -138,6 +138,8 @@ int spvo_destroy(spvo_handle hh) {
     cudaEventDestroy(r.b);
   }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (Handle::GraphEntry& ge : h->graphs)
+    if (ge.exec) cudaGraphExecDestroy(ge.exec);
   for (int i = 0; i < 2; ++i) {
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
@@ -447,7 +449,7 @@ int spvo_stereo_reset(spvo_handle hh) {
   DeviceGuard g(h->device);
   h->has_prev = false;
   if (h->carry_n) CK(cudaMemsetAsync(h->carry_n, 0, sizeof(int), h->stream));
-  if (h->carry_map) CK(cudaMemsetAsync(h->carry_map, 0xFF, (size_t)(h->max_k > 0 ? h->max_k : 1) * sizeof(int), h->stream));
+  if (h->carry_map) CK(cudaMemsetAsync(h->carry_map, 0xFF, (size_t)2 * (h->max_k > 0 ? h->max_k : 1) * sizeof(int), h->stream));
   return SPVO_OK;
 }
 
@@ -469,8 +471,8 @@ static int check_stereo_args(Handle* h, const void* semi, const void* desc, int 
 static int ensure_carry(Handle* h) {
   if (h->carry_desc) return SPVO_OK;
   const size_t K = h->max_k > 0 ? h->max_k : 1;
-  CK(cudaMalloc((void**)&h->carry_map, K * sizeof(int)));
-  CK(cudaMemsetAsync(h->carry_map, 0xFF, K * sizeof(int), h->stream));
+  CK(cudaMalloc((void**)&h->carry_map, 2 * K * sizeof(int)));
+  CK(cudaMemsetAsync(h->carry_map, 0xFF, 2 * K * sizeof(int), h->stream));
   CK(cudaMalloc((void**)&h->carry_desc, K * 256 * sizeof(float)));
   CK(cudaMalloc((void**)&h->carry_kpts, K * sizeof(spvo_keypoint)));
   CK(cudaMalloc((void**)&h->carry_n, sizeof(int)));
@@ -480,35 +482,6 @@ static int ensure_carry(Handle* h) {
 }
 
 // The device pipeline shared by both forms.  desc_out must be a device buffer [2F,K,256].
-struct CopyList {
-  CopySeg seg[8];
-  int n;
-};
-// Several small device-to-device copies in one launch (7 cudaMemcpyAsync nodes cost ~15 us of launch gaps per batch).
-__global__ void __launch_bounds__(256) k_carry_copy(const CopyList L) {
-  // blockIdx.y = segment: all segments (and all of a segment's 16-byte loads) are in flight together
-  const CopySeg g = L.seg[blockIdx.y];
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
-    const uint4* src = static_cast<const uint4*>(g.src);
-    uint4* dst = static_cast<uint4*>(g.dst);
-    const size_t n = g.bytes / 16;
-    for (size_t i = tid; i < n; i += 4 * nth) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i + u * nth < n) v[u] = src[i + u * nth];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i + u * nth < n) dst[i + u * nth] = v[u];
-    }
-  } else {
-    const uint32_t* src = static_cast<const uint32_t*>(g.src);
-    uint32_t* dst = static_cast<uint32_t*>(g.dst);
-    for (size_t i = tid; i < g.bytes / 4; i += nth) dst[i] = src[i];
-  }
-}
-
 static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in_f16, int F, int H, int W,
                            const spvo_stereo_cfg* cfg, spvo_keypoint* kpts, float* desc_out, int* n_kpts,
                            spvo_dmatch* matches, int* n_matches, int* q2t, uint8_t* keep, spvo_quad* quads,
@@ -539,27 +512,34 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
     // the previous batch ran on the exact matcher: convert the carried fp32 descriptors into the carry slot
     CK(tc_prep_problem_operands(h, h->probs + F));
   // !ready: the matcher converts every operand itself (k_tc_prep, bf16) -- decode did not fill the slots
+  if (keep) {  // the row-band / min-disparity test rides in k_finalize_matches (stereo problems = the first F)
+    h->fin_filter.kpts = kpts;
+    h->fin_filter.slot_stride = K;
+    h->fin_filter.nprob = F;
+    h->fin_filter.stereo_threshold = cfg->stereo_threshold;
+    h->fin_filter.min_disparity = cfg->min_disparity;
+    h->fin_filter.keep = keep;
+  }
   rc = run_match(h, h->probs, 2 * F, K, K, &cfg->match, matches, n_matches, q2t, K, ready);
+  h->fin_filter = FilterArgs();
   if (rc) return rc;
-  if (keep)
-    CK(launch_stereo_filter(h, kpts, K, nullptr, nullptr, F, K, matches, n_matches, cfg->stereo_threshold,
-                            cfg->min_disparity, keep));
-  if (quads) CK(launch_consistency(h, F, K, matches, n_matches, q2t, keep, h->carry_map, quads, n_quads));
-  // Carry for the next batch in ONE launch: the previous frame's L<->R map (BASE:475-481) and the last left image
-  // (descriptors, keypoints, count, matcher operand slot) for the next batch's first temporal match.
+  // ONE launch for the tail: the quadruples (BASE:156-207) and, in extra blocks, the carry for the next batch -- the
+  // previous frame's L<->R map (BASE:475-481) and the last left image (descriptors, keypoints, count, matcher operand
+  // slot) for the next batch's first temporal match.  The map is double-buffered: the consistency blocks read the
+  // half written by the previous batch while the copy blocks fill the other one.
+  const size_t mk = (size_t)(h->max_k > 0 ? h->max_k : 1);
+  const int* map_in = h->carry_map + (size_t)h->carry_parity * mk;
+  int* map_out = h->carry_map + (size_t)(h->carry_parity ^ 1) * mk;
   CopyList cl;
   cl.n = 0;
   const size_t last = (size_t)2 * (F - 1);
-  if (q2t) cl.seg[cl.n++] = {q2t + (size_t)(F - 1) * K, h->carry_map, (size_t)K * sizeof(int)};
+  if (q2t) cl.seg[cl.n++] = {q2t + (size_t)(F - 1) * K, map_out, (size_t)K * sizeof(int)};
   cl.seg[cl.n++] = {desc_out + last * K * 256, h->carry_desc, (size_t)K * 256 * sizeof(float)};
   cl.seg[cl.n++] = {kpts + last * K, h->carry_kpts, (size_t)K * sizeof(spvo_keypoint)};
   cl.seg[cl.n++] = {n_kpts + last, h->carry_n, sizeof(int)};
   if (ready) cl.n += tc_copy_slot_segments(h, carry_slot, (int)last, cl.seg + cl.n);
-  {
-    LaunchScope ls(h, KID_CARRY);
-    k_carry_copy<<<dim3(64, cl.n), 256, 0, st>>>(cl);
-  }
-  CK(cudaGetLastError());
+  CK(launch_consistency(h, F, K, matches, n_matches, q2t, keep, map_in, quads, n_quads, cl));
+  if (q2t) h->carry_parity ^= 1;
   h->carry_tc_valid = ready;
   h->has_prev = true;
   return SPVO_OK;
@@ -572,8 +552,71 @@ static int stereo_batch_device_impl(Handle* h, const void* semi, const void* des
   if (!out->desc) return fail(h, SPVO_EINVAL, "stereo_batch_device: desc output is required");
   if (F == 0) return SPVO_OK;
   DeviceGuard g(h->device);
-  return stereo_pipeline(h, semi, desc, in_f16, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
-                         out->n_matches, out->q2t, out->stereo_keep, out->quads, out->n_quads);
+  auto run = [&]() {
+    return stereo_pipeline(h, semi, desc, in_f16, F, H, W, cfg, out->kpts, out->desc, out->n_kpts, out->matches,
+                           out->n_matches, out->q2t, out->stereo_keep, out->quads, out->n_quads);
+  };
+  if (!h->graph_mode || h->profiling || h->decode_subbatches > 1) return run();
+  // Graph mode (the reference's real-time shape: one pair per callback, fixed engine bindings,
+  // visual_odometry_node.cpp:150-262): the call's launches are captured ONCE per signature -- arguments plus the
+  // host-side stream state that selects code paths -- and replayed afterwards; any change re-captures.
+  std::vector<unsigned char> sig;
+  auto put = [&](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    sig.insert(sig.end(), b, b + n);
+  };
+  const int state[8] = {in_f16, F, H, W, h->has_prev ? 1 : 0, h->carry_tc_valid ? 1 : 0, h->carry_parity, 0};
+  put(&semi, sizeof(semi)); put(&desc, sizeof(desc)); put(state, sizeof(state)); put(cfg, sizeof(*cfg));
+  put(out, sizeof(*out)); put(&h->stream, sizeof(h->stream));
+  for (Handle::GraphEntry& ge : h->graphs)
+    if (ge.sig == sig) {
+      CK(cudaGraphLaunch(ge.exec, h->stream));
+      h->launches += ge.kernels;
+      h->has_prev = true;
+      h->carry_tc_valid = ge.ready;
+      if (ge.flips_parity) h->carry_parity ^= 1;
+      return SPVO_OK;
+    }
+  bool seen = false;
+  for (const auto& sg : h->graph_seen) seen = seen || sg == sig;
+  if (!seen) {  // first time: run eagerly, so that every workspace this signature needs exists before a capture
+    if (h->graph_seen.size() >= 16) h->graph_seen.erase(h->graph_seen.begin());
+    h->graph_seen.push_back(sig);
+    return run();
+  }
+  const long long l0 = h->launches;
+  const int parity0 = h->carry_parity;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+  rc = run();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess) return cuda_fail(h, ce, "cudaStreamEndCapture");
+  Handle::GraphEntry ge;
+  ge.sig = sig;
+  ge.kernels = (int)(h->launches - l0);
+  ge.ready = h->carry_tc_valid;
+  ge.flips_parity = h->carry_parity != parity0;
+  const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return cuda_fail(h, ie, "cudaGraphInstantiate");
+  if (h->graphs.size() >= 8) {
+    cudaGraphExecDestroy(h->graphs.front().exec);
+    h->graphs.erase(h->graphs.begin());
+  }
+  h->graphs.push_back(ge);
+  CK(cudaGraphLaunch(ge.exec, h->stream));  // the captured work has not run yet
+  return SPVO_OK;
+}
+
+int spvo_set_graph_mode(spvo_handle hh, int on) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  h->graph_mode = on != 0;
+  return SPVO_OK;
 }
 
 int spvo_stereo_batch_device(spvo_handle hh, const float* semi, const float* desc, int F, int H, int W,
@@ -686,7 +729,7 @@ long long spvo_kernel_launches(spvo_handle hh) {
 static const char* kKernelNames[KID_COUNT] = {
     "k_softmax_heat", "k_detect", "k_sample_desc", "k_dist_exact", "k_row_select", "k_col_select",
     "k_finalize_matches", "k_setup_problems", "k_stereo_filter", "k_tc_prep", "k_tc_gemm", "k_tc_rerank",
-    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency", "k_carry_copy", "k_preprocess"};
+    "k_tc_fallback", "k_tc_fill_dist", "k_tc_triage", "k_desc_planes", "k_desc_normalize", "k_consistency", "k_carry_copy", "k_preprocess"};  // (k_carry_copy: folded into k_consistency)
 
 int spvo_profile_num_kernels(void) { return KID_COUNT; }
 

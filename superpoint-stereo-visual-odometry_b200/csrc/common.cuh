@@ -70,11 +70,24 @@ bool preprocess_geometry(int rows, int cols, int H, int W, int* crop_rows, int* 
 cudaError_t launch_preprocess(Handle* h, const uint8_t* imgs, int B, int rows, int cols, int stride, int H, int W,
                               float* out_f, uint8_t* out_u8);
 
-// One device-to-device copy segment of k_carry_copy (sizes are multiples of 4 bytes).
+// One device-to-device copy segment of the carry copy (sizes are multiples of 4 bytes).
 struct CopySeg {
   const void* src;
   void* dst;
   unsigned long long bytes;
+};
+// Several small device-to-device copies done by extra blocks of k_consistency (one launch for the whole tail).
+struct CopyList {
+  CopySeg seg[8];
+  int n;
+};
+// Stereo row-band / min-disparity test (BASE:169-172) applied by k_finalize_matches to the first `nprob` problems
+// (problem p: keypoint slots 2p and 2p+1), so that the stereo pipeline needs no separate filter launch.
+struct FilterArgs {
+  const spvo_keypoint* kpts = nullptr;
+  int slot_stride = 0, nprob = 0;
+  float stereo_threshold = 0.f, min_disparity = 0.f;
+  uint8_t* keep = nullptr;  // [nprob, out_stride]
 };
 // The three segments (16-bit rows, squared norms, max norm) that copy operand slot src_slot to dst_slot; returns 3.
 int tc_copy_slot_segments(Handle* h, int dst_slot, int src_slot, CopySeg* segs);
@@ -84,9 +97,10 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
                                          int F, int K, int carry_slot);
+// quads == nullptr: only the copies of `cl` run
 cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* matches, const int* n_matches,
                                const int* q2t, const uint8_t* keep, const int* carry_map, spvo_quad* quads,
-                               int* n_quads);
+                               int* n_quads, const CopyList& cl);
 cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
 cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                  const int* q_slot, const int* t_slot, int P, int max_rows,
@@ -142,7 +156,10 @@ struct Handle {
   float* carry_desc = nullptr;      // [max_k, 256]
   spvo_keypoint* carry_kpts = nullptr;
   int* carry_n = nullptr;           // device int; 0 when there is no previous frame
-  int* carry_map = nullptr;         // [max_k] previous frame's L<->R index map (maps_of_indices[PREV_LEFT_PREV_RIGHT])
+  int* carry_map = nullptr;         // [2][max_k] previous frame's L<->R index map (maps_of_indices[PREV_LEFT_PREV_RIGHT]);
+                                    // double-buffered: k_consistency reads one half while its copy blocks fill the other
+  int carry_parity = 0;             // half holding the map of the last processed frame
+  FilterArgs fin_filter;            // consumed by the next k_finalize_matches launch (stereo pipeline)
   spvo_quad* st_quads = nullptr;    // host-form staging
   int* st_nquads = nullptr;
   bool has_prev = false;
@@ -162,6 +179,16 @@ struct Handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   long long launches = 0;
+  // optional CUDA-graph replay of the stereo pipeline (spvo_set_graph_mode): one instantiated graph per call signature
+  struct GraphEntry {
+    std::vector<unsigned char> sig;
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+    bool ready = false, flips_parity = false;
+  };
+  bool graph_mode = false;
+  std::vector<GraphEntry> graphs;
+  std::vector<std::vector<unsigned char>> graph_seen;  // signatures that ran eagerly once (workspaces are sized)
   // optional per-kernel profile
   bool profiling = false;
   std::vector<ProfRec> prof_recs;

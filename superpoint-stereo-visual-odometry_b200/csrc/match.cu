@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(1024)
 k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict__ row_best,
                    const float* __restrict__ row_d, const int* __restrict__ col_best, int max_rows, int max_cols,
                    int mode, float ratio, spvo_dmatch* __restrict__ out, int* __restrict__ n_matches,
-                   int* __restrict__ q2t, int out_stride) {
+                   int* __restrict__ q2t, int out_stride, const FilterArgs flt) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const MatchProblem pr = probs[blockIdx.x];
@@ -182,6 +182,7 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
   if (tid == 0) s_base = 0;
   __syncthreads();
   const bool degenerate = pr.M == 0 || (mode == SPVO_MATCH_KNN_RATIO && pr.M < 2);
+  const bool filter = flt.keep && p < flt.nprob;  // S1 (BASE:169-172) on this problem's matches
   for (int start = 0; start < pr.N; start += 1024) {
     const int i = start + tid;
     bool keep = false;
@@ -205,6 +206,12 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
       spvo_dmatch dm;
       dm.queryIdx = i; dm.trainIdx = tr; dm.imgIdx = 0; dm.distance = d0;
       out[(size_t)p * out_stride + slot] = dm;
+      if (filter) {
+        const spvo_keypoint a = flt.kpts[(size_t)(2 * p) * flt.slot_stride + i];
+        const spvo_keypoint c = flt.kpts[(size_t)(2 * p + 1) * flt.slot_stride + tr];
+        const bool drop = fabsf(__fsub_rn(a.y, c.y)) > flt.stereo_threshold || fabsf(__fsub_rn(a.x, c.x)) < flt.min_disparity;
+        flt.keep[(size_t)p * out_stride + slot] = drop ? 0 : 1;
+      }
     }
     if (q2t && i < pr.N) q2t[(size_t)p * out_stride + i] = keep ? tr : -1;
     __syncthreads();
@@ -216,6 +223,8 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
     __syncthreads();
   }
   if (tid == 0) n_matches[p] = s_base;
+  if (filter)
+    for (int m = s_base + tid; m < out_stride; m += 1024) flt.keep[(size_t)p * out_stride + m] = 0;
 }
 
 __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, const int* n_rows,
@@ -292,13 +301,31 @@ __global__ void k_stereo_filter(const spvo_keypoint* __restrict__ kpts_base, int
   keep[(size_t)p * max_rows + m] = k;
 }
 
+constexpr int kCopyBlocks = 8;  // copy blocks per carry segment
 // Post-match consistency (BASE:156-207): the quadruples solveStereoOdometry triangulates.  Block = frame.
 //   stereo matches of frame f : matches row f        temporal map : q2t row F+f
 //   previous frame's L<->R map: q2t row f-1, or the carried map of the previous batch for f = 0
 __global__ void __launch_bounds__(1024)
 k_consistency(int F, int K, const spvo_dmatch* __restrict__ matches, const int* __restrict__ n_matches,
               const int* __restrict__ q2t, const uint8_t* __restrict__ keep, const int* __restrict__ carry_map,
-              spvo_quad* __restrict__ quads, int* __restrict__ n_quads) {
+              spvo_quad* __restrict__ quads, int* __restrict__ n_quads, const CopyList cl) {
+  if ((int)blockIdx.x >= F) {
+    // copy blocks: the carry for the next batch (last left image's descriptors / keypoints / count / matcher operand,
+    // L<->R map) -- kCopyBlocks blocks per segment, 16-byte accesses where the segment allows
+    const int cb = blockIdx.x - F, segi = cb / kCopyBlocks, blk = cb % kCopyBlocks;
+    const CopySeg g = cl.seg[segi];
+    const size_t tid = (size_t)blk * blockDim.x + threadIdx.x, nth = (size_t)kCopyBlocks * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(g.src) | reinterpret_cast<uintptr_t>(g.dst) | g.bytes) & 15) == 0) {
+      const uint4* src = static_cast<const uint4*>(g.src);
+      uint4* dst = static_cast<uint4*>(g.dst);
+      for (size_t i = tid; i < g.bytes / 16; i += nth) dst[i] = src[i];
+    } else {
+      const uint32_t* src = static_cast<const uint32_t*>(g.src);
+      uint32_t* dst = static_cast<uint32_t*>(g.dst);
+      for (size_t i = tid; i < g.bytes / 4; i += nth) dst[i] = src[i];
+    }
+    return;
+  }
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -372,7 +399,8 @@ cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, in
   {
     LaunchScope ls(h, KID_FINALIZE);
     k_finalize_matches<<<P, 1024, 0, h->stream>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode,
-                                                  cfg.ratio, out, n_matches, q2t, out_stride);
+                                                  cfg.ratio, out, n_matches, q2t, out_stride, h->fin_filter);
+    h->fin_filter = FilterArgs();  // one-shot
   }
   return cudaGetLastError();
 }
@@ -430,10 +458,12 @@ cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const f
 
 cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* matches, const int* n_matches,
                                const int* q2t, const uint8_t* keep, const int* carry_map, spvo_quad* quads,
-                               int* n_quads) {
-  if (F == 0) return cudaSuccess;
+                               int* n_quads, const CopyList& cl) {
+  const int fb = quads ? F : 0;  // frames whose quadruples are wanted
+  if (fb + cl.n == 0) return cudaSuccess;
   LaunchScope ls(h, KID_CONSISTENCY);
-  k_consistency<<<F, 1024, 0, h->stream>>>(F, K, matches, n_matches, q2t, keep, carry_map, quads, n_quads);
+  k_consistency<<<fb + cl.n * kCopyBlocks, 1024, 0, h->stream>>>(fb, K, matches, n_matches, q2t, keep, carry_map, quads,
+                                                                 n_quads, cl);
   return cudaGetLastError();
 }
 

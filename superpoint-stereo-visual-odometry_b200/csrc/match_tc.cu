@@ -42,6 +42,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <limits.h>
 
 #include "common.cuh"
@@ -952,17 +953,26 @@ k_tc_fill_dist(const MatchProblem* __restrict__ probs, int mode, int max_rows, i
 // scanned exactly (counters[2]).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFbRows = 8;
+constexpr int kFbSplit = 4;             // CTAs (one thread-block cluster) per directed problem: each scans a quarter of the columns
+constexpr int kFbVW = 8 * kFbSplit;     // "virtual warps" of a cluster
+constexpr int kFbCand = 3 * kFbVW / 32; // shortlisted columns per lane in the finishing step
 
 __global__ void __launch_bounds__(256, 2)
 k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm, int cap,
               int max_rows, int max_cols, const int* __restrict__ fb_count, const int* __restrict__ fb_list,
               int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
               unsigned long long* __restrict__ counters) {
-  __shared__ float s_v[8][kFbRows][3];
-  __shared__ int s_j[8][kFbRows][3];
-  const int dp = blockIdx.x, p = dp < P ? dp : dp - P;
+  // The scan of a queued row group is latency-bound per CTA (a warp keeps two train rows in flight), so the columns
+  // are split over a cluster of kFbSplit CTAs; their per-warp shortlists meet in the shared memory of cluster rank 0
+  // (distributed shared memory), which finishes the rows.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float s_v[kFbVW][kFbRows][3];
+  __shared__ int s_j[kFbVW][kFbRows][3];
+  const int crank = (int)cluster.block_rank();
+  const int dp = blockIdx.x / kFbSplit, p = dp < P ? dp : dp - P;
   const int nfb = fb_count[dp];
-  if (nfb == 0) return;
+  if (nfb == 0) return;  // uniform over the cluster
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
   const int Nb = rev ? pr.N : pr.M;
@@ -972,7 +982,10 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
   const float* nbv = nrm + (size_t)b_op * cap;
   const bool knn = (mode == SPVO_MATCH_KNN_RATIO) && !rev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-  const int myr = lane >> 2;  // after the butterfly, lanes 4r..4r+3 hold row r's dot product
+  const int vw = crank * 8 + warp;  // this warp takes columns vw, vw + 32, vw + 64, ...
+  const int myr = lane >> 2;        // after the butterfly, lanes 4r..4r+3 hold row r's dot product
+  float* rv = cluster.map_shared_rank(&s_v[0][0][0], 0);
+  int* rj = cluster.map_shared_rank(&s_j[0][0][0], 0);
 
   for (int r0 = 0; r0 < nfb; r0 += kFbRows) {
     const int nr = min(kFbRows, nfb - r0);
@@ -994,24 +1007,24 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
     auto load_cols = [&](int jb, float4* x, float4* y, float* nb) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const int j = min(jb + 8 * u, Nb - 1);
+        const int j = min(jb + kFbVW * u, Nb - 1);
         x[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane);
         y[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)j * kDim) + 2 * lane + 1);
         nb[u] = __ldg(nbv + j);
       }
     };
-    if (warp < Nb) load_cols(warp, xn, yn, nbn);
-    for (int jb = warp; jb < Nb; jb += 8 * kU) {
+    if (vw < Nb) load_cols(vw, xn, yn, nbn);
+    for (int jb = vw; jb < Nb; jb += kFbVW * kU) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         xs[u] = xn[u];
         ys[u] = yn[u];
         nbs[u] = nbn[u];
       }
-      if (jb + 8 * kU < Nb) load_cols(jb + 8 * kU, xn, yn, nbn);
+      if (jb + kFbVW * kU < Nb) load_cols(jb + kFbVW * kU, xn, yn, nbn);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const int j = jb + 8 * u;
+        const int j = jb + kFbVW * u;
         const float b[8] = {xs[u].x, xs[u].y, xs[u].z, xs[u].w, ys[u].x, ys[u].y, ys[u].z, ys[u].w};
         float pd[kFbRows];
 #pragma unroll
@@ -1050,22 +1063,32 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         }
       }
     }
-    if ((lane & 3) == 0) {
+    if ((lane & 3) == 0) {  // into rank 0's shared memory
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        s_v[warp][myr][k] = v[k];
-        s_j[warp][myr][k] = ix[k];
+        rv[(vw * kFbRows + myr) * 3 + k] = v[k];
+        rj[(vw * kFbRows + myr) * 3 + k] = ix[k];
       }
     }
-    __syncthreads();
-    // warp w finishes row w of the group: 24 shortlisted columns (3 per warp)
-    if (warp < nr) {
+    cluster.sync();
+    // rank 0, warp w finishes row w of the group: 3 shortlisted columns per virtual warp
+    if (crank == 0 && warp < nr) {
       const int i = fb_list[(size_t)dp * cap + r0 + warp];
       const float* arow = A + (size_t)i * kDim;
       const float na = nrm[(size_t)a_op * cap + i];
-      const float cv = lane < 24 ? s_v[lane / 3][warp][lane % 3] : INFINITY;
-      const int cj = lane < 24 ? s_j[lane / 3][warp][lane % 3] : -1;
-      float m0 = cv, m1 = INFINITY, bm = (cj >= 0) ? nbv[cj] : 0.f;
+      float cv[kFbCand];
+      int cj[kFbCand];
+      float m0 = INFINITY, m1 = INFINITY, bm = 0.f;
+#pragma unroll
+      for (int t = 0; t < kFbCand; ++t) {
+        const int idx = lane + 32 * t;
+        cv[t] = s_v[idx / 3][warp][idx % 3];
+        cj[t] = s_j[idx / 3][warp][idx % 3];
+        if (cj[t] >= 0) bm = fmaxf(bm, nbv[cj[t]]);
+        const float hi = fmaxf(m0, cv[t]);
+        m0 = fminf(m0, cv[t]);
+        m1 = fminf(m1, hi);
+      }
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         const float c0 = __shfl_xor_sync(0xffffffffu, m0, o), c1 = __shfl_xor_sync(0xffffffffu, m1, o);
@@ -1076,9 +1099,14 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
       }
       const float eps32 = 4e-5f * (na + bm);  // >= 2 * (256 + 8) * 2^-24 |a||b| plus the final roundings
       const float thr = (knn ? m1 : m0) + 2.0f * eps32;
-      const bool cand = cj >= 0 && cv <= thr;
-      // a warp's third entry inside the threshold means that warp may have dropped a near-tie
-      const bool overflow = __any_sync(0xffffffffu, cand && (lane % 3) == 2 && Nb > 24);
+      bool cand[kFbCand], over = false;
+#pragma unroll
+      for (int t = 0; t < kFbCand; ++t) {
+        cand[t] = cj[t] >= 0 && cv[t] <= thr;
+        // a warp's third entry inside the threshold means that warp may have dropped a near-tie
+        over |= cand[t] && ((lane + 32 * t) % 3) == 2 && Nb > 3 * kFbVW;
+      }
+      const bool overflow = __any_sync(0xffffffffu, over);
       float b0 = INFINITY, b1 = INFINITY;
       int x0 = INT_MAX, x1 = INT_MAX;
       if (overflow) {
@@ -1089,19 +1117,22 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         }
         if (lane == 0) atomicAdd(&counters[2], 1ull);
       } else {
-        unsigned pending = __ballot_sync(0xffffffffu, cand);
-        while (pending) {  // two candidate columns per step, one per half warp
-          const int s0 = __ffs(pending) - 1;
-          pending &= pending - 1;
-          int s1 = s0;
-          if (pending) {
-            s1 = __ffs(pending) - 1;
+#pragma unroll
+        for (int t = 0; t < kFbCand; ++t) {
+          unsigned pending = __ballot_sync(0xffffffffu, cand[t]);
+          while (pending) {  // two candidate columns per step, one per half warp
+            const int s0 = __ffs(pending) - 1;
             pending &= pending - 1;
+            int s1 = s0;
+            if (pending) {
+              s1 = __ffs(pending) - 1;
+              pending &= pending - 1;
+            }
+            const int ja = __shfl_sync(0xffffffffu, cj[t], s0), jb = __shfl_sync(0xffffffffu, cj[t], s1);
+            const int j = half ? jb : ja;
+            const float d = exact_dist_half(arow, B + (size_t)j * kDim, l16);
+            if (half == 0 || s1 != s0) top2_push(d, j, b0, x0, b1, x1);
           }
-          const int ja = __shfl_sync(0xffffffffu, cj, s0), jb = __shfl_sync(0xffffffffu, cj, s1);
-          const int j = half ? jb : ja;
-          const float d = exact_dist_half(arow, B + (size_t)j * kDim, l16);
-          if (half == 0 || s1 != s0) top2_push(d, j, b0, x0, b1, x1);
         }
       }
       const float c0 = __shfl_xor_sync(0xffffffffu, b0, 16), c1 = __shfl_xor_sync(0xffffffffu, b1, 16);
@@ -1124,7 +1155,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         }
       }
     }
-    __syncthreads();
+    cluster.sync();  // rank 0 has consumed the shortlists: the next group may overwrite them
   }
 }
 
@@ -1333,8 +1364,22 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
-      k_tc_fallback<<<ndir, 256, 0, st>>>(probs, P, cfg.mode, w->nrm, cap, mr, mc, fb_count, w->fb_list,
-                                          h->row_best, h->row_d, h->col_best, h->counters);
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(ndir * kFbSplit);
+      lc.blockDim = dim3(256);
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kFbSplit;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      const int* fbc = fb_count;
+      const int* fbl = w->fb_list;
+      if ((e = cudaLaunchKernelEx(&lc, k_tc_fallback, probs, P, (int)cfg.mode, (const float*)w->nrm, cap, mr, mc, fbc, fbl,
+                                  h->row_best, h->row_d, h->col_best, h->counters)) != cudaSuccess)
+        return e;
     }
     if (cfg.mode != SPVO_MATCH_KNN_RATIO) {
       LaunchScope ls(h, KID_TC_FILL);

@@ -193,6 +193,10 @@ class Frontend:
     def stereo_reset(self):
         self._check(self._L.spvo_stereo_reset(self._h))
 
+    def set_graph_mode(self, on: bool = True):
+        """CUDA-graph replay of stereo_batch_device calls with an unchanged signature (spvo_set_graph_mode)."""
+        self._check(self._L.spvo_set_graph_mode(self._h, int(on)))
+
     @staticmethod
     def _stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
                     stereo_threshold, min_disparity):

@@ -142,3 +142,45 @@ def test_stereo_batch_odd_keypoint_budget(spvo, oracle, K):
                             algorithm=alg)
             _check_batch(S, out, ref, b * F, F, K)
         fe.close()
+
+
+def test_graph_mode_replays_identically(spvo):
+    """spvo_set_graph_mode: one pair per call into FIXED bindings (the reference's real-time loop,
+    visual_odometry_node.cpp:150-262).  The captured graphs must reproduce the plain launches bit for bit over a
+    sequence that includes a reset, and the signature changes (other buffers) must re-capture, not misfire."""
+    import torch
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, NF = 192, 640, 500, 14
+    dev = torch.device("cuda", 0)
+    semi, desc = synth.make_stream(NF, H, W, seed=9, device=dev)
+    kw = dict(max_keypoints=K, mode=1, stereo_threshold=2.0, min_disparity=0.25)
+
+    def run(graph):
+        fe = S.Frontend(0, 2, H, W, K)
+        fe.set_stream(torch.cuda.current_stream().cuda_stream)
+        fe.set_graph_mode(graph)
+        bs, bd = torch.empty_like(semi[0]), torch.empty_like(desc[0])      # the engine's fixed output bindings
+        bs2, bd2 = torch.empty_like(semi[0]), torch.empty_like(desc[0])    # a second set (signature change)
+        out = fe.alloc_stereo_out(1, K, device=dev)
+        res = []
+        for f in range(NF):
+            if f == 9:
+                fe.stereo_reset()
+            s_, d_ = (bs2, bd2) if f in (5, 6) else (bs, bd)
+            s_.copy_(semi[f])
+            d_.copy_(desc[f])
+            fe.stereo_batch_device(s_, d_, 1, H, W, out, **kw)
+            torch.cuda.synchronize()
+            res.append({k: v.cpu().numpy().copy() for k, v in out.items()})
+        launches = fe.kernel_launches
+        fe.close()
+        return res, launches
+
+    plain, l0 = run(False)
+    graph, l1 = run(True)
+    assert l0 == l1, "replays must account for the same kernel launches"
+    for f, (a, b) in enumerate(zip(plain, graph)):
+        for k in a:
+            assert a[k].tobytes() == b[k].tobytes(), (f, k)
+    assert plain[3]["n_matches"][1] > 50 and plain[9]["n_matches"][1] == 0  # temporal matches; none right after a reset
