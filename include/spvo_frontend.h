@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPVO_ABI_VERSION 3
+#define SPVO_ABI_VERSION 4
 
 #define SPVO_DESC_DIM 256      /* output_desc_channel_, HPP:359 */
 #define SPVO_DET_CHANNELS 65   /* output_det_channel_,  HPP:355 */
@@ -84,11 +84,20 @@ enum {
                                   decode produces) + exact fp32 re-rank; identical results */
 };
 
+/* Flags (spvo_match_cfg.flags).  ROW_BAND = the BASELINE north star's "left<->right matching under a stereo row-band
+ * constraint" as an explicit opt-in: train row j is a candidate of query i only if |y_i - y_j| <= band.  The reference
+ * matches UNMASKED and applies the band afterwards (BASE:169-172), and cv::BFMatcher refuses crossCheck with a mask, so
+ * the masked cross-check is defined as two masked cv::BFMatcher(NORM_L2, false)::match calls (mask, transposed mask)
+ * plus a mutual test -- what the oracle is pinned to.  A query without an allowed train row has no match; KNN_RATIO
+ * needs two allowed rows.  In spvo_stereo_batch* the flag masks the L<->R problems with band = stereo_threshold (the
+ * temporal problems stay unmasked); for single problems use spvo_match_masked[_device]. */
+#define SPVO_MATCH_FLAG_ROW_BAND 1
+
 typedef struct spvo_match_cfg {
   int32_t mode;      /* SPVO_MATCH_* */
   float ratio;       /* knn_threshold_ = 0.8f (HPP:137); used by SPVO_MATCH_KNN_RATIO */
   int32_t algorithm; /* SPVO_MATCHER_* */
-  int32_t reserved;
+  int32_t flags;     /* SPVO_MATCH_FLAG_* (0 = the reference's behaviour) */
 } spvo_match_cfg;
 
 typedef struct spvo_handle_s* spvo_handle;
@@ -152,6 +161,15 @@ int spvo_match(spvo_handle h, const float* q, int N, const float* t, int M, int 
 /* Device-pointer form; n_matches is a device int; asynchronous. */
 int spvo_match_device(spvo_handle h, const float* q, int N, const float* t, int M, int dim,
                       const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t);
+
+/* Row-band masked matching of one problem (see SPVO_MATCH_FLAG_ROW_BAND): q_kpts [N], t_kpts [M] are the keypoints the
+ * descriptors belong to (only .y is read); band >= 0.  Same outputs as spvo_match. */
+int spvo_match_masked(spvo_handle h, const float* q, int N, const float* t, int M, int dim,
+                      const spvo_match_cfg* cfg, const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band,
+                      spvo_dmatch* out, int* n_matches, int* q2t);
+int spvo_match_masked_device(spvo_handle h, const float* q, int N, const float* t, int M, int dim,
+                             const spvo_match_cfg* cfg, const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts,
+                             float band, spvo_dmatch* out, int* n_matches, int* q2t);
 
 /* Batched device form: P independent problems per launch (frames are independent in the front
  * end, so a stream of stereo pairs becomes grouped launches).  Problem p matches

@@ -124,7 +124,7 @@ class FeatureFrontEnd {
                                                    : (cross_check_ ? SPVO_MATCH_NN_CROSSCHECK : SPVO_MATCH_NN);
     cfg.ratio = knn_threshold_;
     cfg.algorithm = SPVO_MATCHER_AUTO;
-    cfg.reserved = 0;
+    cfg.flags = 0;
     cv_Dmatches.assign((size_t)(N > 0 ? N : 1), DMatch());
     std::vector<int> q2t((size_t)(N > 0 ? N : 1), -1);
     int n = 0;

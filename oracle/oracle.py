@@ -59,6 +59,9 @@ def lib():
         L.spvo_oracle_match.restype = C.c_int
         L.spvo_oracle_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp,
                                         C.c_int]
+        L.spvo_oracle_match_masked.restype = C.c_int
+        L.spvo_oracle_match_masked.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_float,
+                                               vp, vp, vp, C.c_int]
         L.spvo_oracle_stereo_filter.restype = C.c_int
         L.spvo_oracle_stereo_filter.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
         L.spvo_oracle_consistency.restype = C.c_int
@@ -152,8 +155,8 @@ def decode(semi, desc, conf_thresh=0.015, dist_thresh=4, border_remove=4, max_ke
     return dict(kpts=kp, desc=dout, n=n, scores=scores, walked=walked, ncand=ncand, heat=heat)
 
 
-def match(q, t, mode=MODE_NN_CROSSCHECK, ratio=0.8, num_threads=1):
-    """Returns (matches structured [n], q2t [N])."""
+def match(q, t, mode=MODE_NN_CROSSCHECK, ratio=0.8, num_threads=1, qy=None, ty=None, band=-1.0):
+    """Returns (matches structured [n], q2t [N]).  qy / ty / band: optional row-band mask |qy[i] - ty[j]| <= band."""
     q = _f32(q).reshape(-1, q.shape[-1] if q.ndim > 1 else 256)
     t = _f32(t).reshape(-1, t.shape[-1] if t.ndim > 1 else 256)
     N, D = q.shape
@@ -161,8 +164,11 @@ def match(q, t, mode=MODE_NN_CROSSCHECK, ratio=0.8, num_threads=1):
     out = np.zeros(max(N, 1), DMATCH_DTYPE)
     q2t = np.full(max(N, 1), -1, np.int32)
     n = C.c_int(0)
-    rc = lib().spvo_oracle_match(_p(q), N, _p(t), M, D, int(mode), float(ratio), _p(out), C.byref(n), _p(q2t),
-                                 int(num_threads))
+    if qy is not None:
+        qy, ty = _f32(qy).reshape(-1), _f32(ty).reshape(-1)
+        assert qy.size == N and ty.size == M
+    rc = lib().spvo_oracle_match_masked(_p(q), N, _p(t), M, D, int(mode), float(ratio), _p(qy), _p(ty), float(band),
+                                        _p(out), C.byref(n), _p(q2t), int(num_threads))
     if rc != 0:
         raise ValueError("spvo_oracle_match: invalid arguments")
     return out[: n.value].copy(), q2t[:N].copy()

@@ -428,22 +428,34 @@ int spvo_oracle_decode(const float* semi, const float* desc, int B, int H, int W
 // Output DMatch list in ascending queryIdx, imgIdx = 0; q2t[N] = trainIdx or -1 (:483-491).
 // Defined edge cases (the reference has UB / throws): N==0 or M==0 -> 0 matches; mode 2 with
 // M < 2 -> 0 matches.
-int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int mode, float ratio,
-                      spvo_dmatch* out, int* n_matches, int* q2t, int num_threads) {
+// Matching with an optional ROW-BAND MASK (BASELINE north star: "run left<->right under a stereo row-band constraint").
+// The reference itself matches unmasked and applies |y_l - y_r| <= stereo_threshold afterwards
+// (feature_detection_base.cpp:169-172); cv::BFMatcher rejects crossCheck together with a mask, so the masked
+// cross-check is DEFINED as what two masked cv::BFMatcher(NORM_L2, false)::match calls (query->train with the mask,
+// train->query with its transpose) plus a manual mutual test give -- pinned against cv2 in tests/test_oracle_match.py.
+//   allowed(i, j) = |qy[i] - ty[j]| <= band      (band < 0 or qy == NULL: no mask)
+// A query with no allowed train row has no match; kNN-ratio needs two allowed rows (BASE:469 would be UB).
+int spvo_oracle_match_masked(const float* q, int N, const float* t, int M, int dim, int mode, float ratio,
+                             const float* qy, const float* ty, float band, spvo_dmatch* out, int* n_matches,
+                             int* q2t, int num_threads) {
   if (N < 0 || M < 0 || dim <= 0 || !n_matches || mode < 0 || mode > 2) return 1;
   *n_matches = 0;
   if (q2t) for (int i = 0; i < N; ++i) q2t[i] = -1;
   if (N == 0 || M == 0) return 0;
   if (mode == 2 && M < 2) return 0;
-  std::vector<int> best(N, -1), tbest;
+  const bool masked = qy && ty && band >= 0.0f;
+  auto allowed = [&](int i, int j) { return !masked || std::fabs(qy[i] - ty[j]) <= band; };
+  std::vector<int> best(N, -1), tbest, nallowed(N, 0);
   std::vector<float> d0(N, 0.f), d1(N, 0.f);
   run_parallel(N, num_threads, [&](int lo, int hi) {
     for (int i = lo; i < hi; ++i) {
       const float* a = q + (size_t)i * dim;
       // cv::batchDistance top-K insertion: strict '<' keeps the first index on ties, stable for K=2.
       float b0 = INFINITY, b1 = INFINITY;
-      int i0 = -1;
+      int i0 = -1, na = 0;
       for (int j = 0; j < M; ++j) {
+        if (!allowed(i, j)) continue;
+        ++na;
         float d = l2dist_cv(a, t + (size_t)j * dim, dim);
         if (d < b0 || i0 < 0) {
           if (i0 >= 0) b1 = b0;
@@ -456,6 +468,7 @@ int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int
       best[i] = i0;
       d0[i] = b0;
       d1[i] = b1;
+      nallowed[i] = na;
     }
   });
   if (mode == 1) {
@@ -466,6 +479,7 @@ int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int
         float b0 = INFINITY;
         int i0 = -1;
         for (int i = 0; i < N; ++i) {
+          if (!allowed(i, j)) continue;
           float d = l2dist_cv(a, q + (size_t)i * dim, dim);
           if (d < b0 || i0 < 0) {
             b0 = d;
@@ -478,9 +492,9 @@ int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int
   }
   int n = 0;
   for (int i = 0; i < N; ++i) {
-    bool keep = true;
-    if (mode == 1) keep = (tbest[best[i]] == i);
-    if (mode == 2) keep = (d0[i] < ratio * d1[i]);
+    bool keep = best[i] >= 0;
+    if (keep && mode == 1) keep = (tbest[best[i]] == i);
+    if (keep && mode == 2) keep = nallowed[i] >= 2 && (d0[i] < ratio * d1[i]);
     if (!keep) continue;
     if (out) out[n] = {i, best[i], 0, d0[i]};
     if (q2t) q2t[i] = best[i];
@@ -488,6 +502,12 @@ int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int
   }
   *n_matches = n;
   return 0;
+}
+
+int spvo_oracle_match(const float* q, int N, const float* t, int M, int dim, int mode, float ratio,
+                      spvo_dmatch* out, int* n_matches, int* q2t, int num_threads) {
+  return spvo_oracle_match_masked(q, N, t, M, dim, mode, ratio, nullptr, nullptr, -1.0f, out, n_matches, q2t,
+                                  num_threads);
 }
 
 // S1: stereo row-band / min-disparity test applied to L<->R matches

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libspvo_frontend.so")
 SPVO_OK, SPVO_EINVAL, SPVO_ECUDA, SPVO_ENODEVICE, SPVO_ENOMEM = 0, 1, 2, 3, 4
 MATCH_NN, MATCH_NN_CROSSCHECK, MATCH_KNN_RATIO = 0, 1, 2
 MATCHER_AUTO, MATCHER_EXACT_FP32, MATCHER_TENSOR = 0, 1, 2
+MATCH_FLAG_ROW_BAND = 1
 
 KEYPOINT_DTYPE = np.dtype(
     [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
@@ -27,7 +28,7 @@ class DecodeCfg(C.Structure):
 
 
 class MatchCfg(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("ratio", C.c_float), ("algorithm", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("mode", C.c_int32), ("ratio", C.c_float), ("algorithm", C.c_int32), ("flags", C.c_int32)]
 
 
 class StereoCfg(C.Structure):
@@ -44,7 +45,7 @@ class StereoOut(C.Structure):
 # every symbol include/spvo_frontend.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
     "spvo_create", "spvo_destroy", "spvo_last_error", "spvo_abi_version", "spvo_set_stream", "spvo_sync",
-    "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_batch_device",
+    "spvo_preprocess", "spvo_preprocess_device", "spvo_decode", "spvo_decode_device", "spvo_match", "spvo_match_device", "spvo_match_masked", "spvo_match_masked_device", "spvo_match_batch_device",
     "spvo_stereo_filter_batch_device", "spvo_stereo_reset", "spvo_set_graph_mode", "spvo_stereo_batch_device", "spvo_stereo_batch",
     "spvo_decode_f16", "spvo_decode_device_f16", "spvo_stereo_batch_f16", "spvo_stereo_batch_device_f16",
     "spvo_kernel_launches", "spvo_debug_counters", "spvo_debug_div_check", "spvo_profile_enable", "spvo_profile_num_kernels",
@@ -81,6 +82,11 @@ def load():
     mat = [vp, vp, ci, vp, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
     L.spvo_match.argtypes = mat
     L.spvo_match_device.argtypes = mat
+    mmat = [vp, vp, ci, vp, ci, ci, C.POINTER(MatchCfg), vp, vp, cf, vp, vp, vp]
+    L.spvo_match_masked.argtypes = mmat
+    L.spvo_match_masked_device.argtypes = mmat
+    L.spvo_match_masked.restype = ci
+    L.spvo_match_masked_device.restype = ci
     L.spvo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(MatchCfg), vp, vp, vp]
     L.spvo_stereo_filter_batch_device.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp, vp, cf, cf, vp]
     L.spvo_stereo_reset.argtypes = [vp]
@@ -104,7 +110,7 @@ def load():
     L.spvo_profile_read.argtypes = [vp, vp, vp, ci]
     L.spvo_profile_read.restype = ci
     for name in ("spvo_create", "spvo_destroy", "spvo_set_stream", "spvo_sync", "spvo_decode", "spvo_decode_device",
-                 "spvo_match", "spvo_match_device", "spvo_match_batch_device", "spvo_stereo_filter_batch_device",
+                 "spvo_match", "spvo_match_device", "spvo_match_masked", "spvo_match_masked_device", "spvo_match_batch_device", "spvo_stereo_filter_batch_device",
                  "spvo_debug_counters", "spvo_stereo_reset", "spvo_stereo_batch_device", "spvo_stereo_batch"):
         getattr(L, name).restype = ci
     _lib = L

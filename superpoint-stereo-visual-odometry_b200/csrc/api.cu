@@ -129,7 +129,7 @@ int spvo_destroy(spvo_handle hh) {
   tc_workspace_free(h);
   void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->cand_list, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
-                  h->st_matches, h->st_q2t, h->st_nm, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
+                  h->st_matches, h->st_q2t, h->st_nm, h->st_mkp, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -330,6 +330,7 @@ static int check_match_cfg(Handle* h, const spvo_match_cfg* cfg, int dim) {
   if (cfg->mode < SPVO_MATCH_NN || cfg->mode > SPVO_MATCH_KNN_RATIO) return fail(h, SPVO_EINVAL, "match: mode %d", cfg->mode);
   if (cfg->algorithm < SPVO_MATCHER_AUTO || cfg->algorithm > SPVO_MATCHER_TENSOR)
     return fail(h, SPVO_EINVAL, "match: algorithm %d", cfg->algorithm);
+  if (cfg->flags & ~SPVO_MATCH_FLAG_ROW_BAND) return fail(h, SPVO_EINVAL, "match: unknown flags 0x%x", cfg->flags);
   return SPVO_OK;
 }
 
@@ -353,22 +354,39 @@ static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, 
   return SPVO_OK;
 }
 
-int spvo_match_device(spvo_handle hh, const float* q, int N, const float* t, int M, int dim,
-                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t) {
-  Handle* h = reinterpret_cast<Handle*>(hh);
+static int match_device_impl(Handle* h, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
+                             const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band, spvo_dmatch* out,
+                             int* n_matches, int* q2t) {
   if (!h) return SPVO_EINVAL;
   int rc = check_match_cfg(h, cfg, dim);
   if (rc) return rc;
   if (N < 0 || M < 0 || !n_matches || (N > 0 && (!q || !out)) || (M > 0 && !t))
     return fail(h, SPVO_EINVAL, "match: bad arguments (N %d, M %d)", N, M);
   DeviceGuard g(h->device);
-  CK(launch_set_problem(h, h->probs, q, N, t, M));
-  return run_match(h, h->probs, 1, N, M, cfg, out, n_matches, q2t, N > 0 ? N : 1);
+  spvo_match_cfg c = *cfg;
+  c.flags = (q_kpts && t_kpts && band >= 0.0f) ? (c.flags | SPVO_MATCH_FLAG_ROW_BAND) : (c.flags & ~SPVO_MATCH_FLAG_ROW_BAND);
+  CK(launch_set_problem(h, h->probs, q, N, t, M, q_kpts, t_kpts, band));
+  return run_match(h, h->probs, 1, N, M, &c, out, n_matches, q2t, N > 0 ? N : 1);
 }
 
-int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
-               spvo_dmatch* out, int* n_matches, int* q2t) {
+int spvo_match_device(spvo_handle hh, const float* q, int N, const float* t, int M, int dim,
+                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t) {
+  return match_device_impl(reinterpret_cast<Handle*>(hh), q, N, t, M, dim, cfg, nullptr, nullptr, -1.0f, out, n_matches,
+                           q2t);
+}
+
+int spvo_match_masked_device(spvo_handle hh, const float* q, int N, const float* t, int M, int dim,
+                             const spvo_match_cfg* cfg, const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts,
+                             float band, spvo_dmatch* out, int* n_matches, int* q2t) {
   Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  if (!q_kpts || !t_kpts || !(band >= 0.0f)) return fail(h, SPVO_EINVAL, "match_masked: keypoints and band >= 0 are required");
+  return match_device_impl(h, q, N, t, M, dim, cfg, q_kpts, t_kpts, band, out, n_matches, q2t);
+}
+
+static int match_host_impl(Handle* h, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
+                           const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band, spvo_dmatch* out,
+                           int* n_matches, int* q2t) {
   if (!h) return SPVO_EINVAL;
   int rc = check_match_cfg(h, cfg, dim);
   if (rc) return rc;
@@ -380,7 +398,8 @@ int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int
   cudaStream_t st = h->stream;
   const size_t rows = (size_t)(N > M ? N : M);
   if (h->st_rows < rows) {
-    void** ps[] = {(void**)&h->st_q, (void**)&h->st_t, (void**)&h->st_matches, (void**)&h->st_q2t, (void**)&h->st_nm};
+    void** ps[] = {(void**)&h->st_q, (void**)&h->st_t, (void**)&h->st_matches, (void**)&h->st_q2t, (void**)&h->st_nm,
+                   (void**)&h->st_mkp};
     for (void** p : ps) {
       if (*p) cudaFree(*p);
       *p = nullptr;
@@ -391,12 +410,22 @@ int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int
     CK(cudaMalloc((void**)&h->st_matches, rows * sizeof(spvo_dmatch)));
     CK(cudaMalloc((void**)&h->st_q2t, rows * sizeof(int)));
     CK(cudaMalloc((void**)&h->st_nm, sizeof(int)));
+    CK(cudaMalloc((void**)&h->st_mkp, 2 * rows * sizeof(spvo_keypoint)));
     h->st_rows = rows;
   }
+  const bool masked = q_kpts && t_kpts && band >= 0.0f;
+  spvo_keypoint* d_qk = masked ? h->st_mkp : nullptr;
+  spvo_keypoint* d_tk = masked ? h->st_mkp + rows : nullptr;
   CK(cudaMemcpyAsync(h->st_q, q, (size_t)N * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
   if (M > 0) CK(cudaMemcpyAsync(h->st_t, t, (size_t)M * 256 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(launch_set_problem(h, h->probs, h->st_q, N, h->st_t, M));
-  rc = run_match(h, h->probs, 1, N, M, cfg, h->st_matches, h->st_nm, h->st_q2t, N);
+  if (masked) {
+    CK(cudaMemcpyAsync(d_qk, q_kpts, (size_t)N * sizeof(spvo_keypoint), cudaMemcpyHostToDevice, st));
+    if (M > 0) CK(cudaMemcpyAsync(d_tk, t_kpts, (size_t)M * sizeof(spvo_keypoint), cudaMemcpyHostToDevice, st));
+  }
+  spvo_match_cfg c = *cfg;
+  c.flags = masked ? (c.flags | SPVO_MATCH_FLAG_ROW_BAND) : (c.flags & ~SPVO_MATCH_FLAG_ROW_BAND);
+  CK(launch_set_problem(h, h->probs, h->st_q, N, h->st_t, M, d_qk, d_tk, band));
+  rc = run_match(h, h->probs, 1, N, M, &c, h->st_matches, h->st_nm, h->st_q2t, N);
   if (rc) return rc;
   CK(cudaMemcpyAsync(n_matches, h->st_nm, sizeof(int), cudaMemcpyDeviceToHost, st));
   if (q2t) CK(cudaMemcpyAsync(q2t, h->st_q2t, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -404,6 +433,22 @@ int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int
   if (*n_matches > 0)
     CK(cudaMemcpy(out, h->st_matches, (size_t)*n_matches * sizeof(spvo_dmatch), cudaMemcpyDeviceToHost));
   return SPVO_OK;
+}
+
+int spvo_match(spvo_handle hh, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
+               spvo_dmatch* out, int* n_matches, int* q2t) {
+  return match_host_impl(reinterpret_cast<Handle*>(hh), q, N, t, M, dim, cfg, nullptr, nullptr, -1.0f, out, n_matches,
+                         q2t);
+}
+
+int spvo_match_masked(spvo_handle hh, const float* q, int N, const float* t, int M, int dim, const spvo_match_cfg* cfg,
+                      const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band, spvo_dmatch* out,
+                      int* n_matches, int* q2t) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return SPVO_EINVAL;
+  if (N > 0 && M > 0 && (!q_kpts || !t_kpts || !(band >= 0.0f)))
+    return fail(h, SPVO_EINVAL, "match_masked: keypoints and band >= 0 are required");
+  return match_host_impl(h, q, N, t, M, dim, cfg, q_kpts, t_kpts, band, out, n_matches, q2t);
 }
 
 int spvo_match_batch_device(spvo_handle hh, const float* desc_base, const int* n_rows, int slot_stride_rows,
@@ -506,7 +551,9 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
     CK(cudaMalloc((void**)&h->probs, (size_t)2 * F * sizeof(MatchProblem)));
     h->probs_cap = 2 * F;
   }
-  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot));
+  const bool band = (cfg->match.flags & SPVO_MATCH_FLAG_ROW_BAND) != 0;  // L<->R under the row band (opt-in)
+  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot, band ? kpts : nullptr,
+                                  band ? cfg->stereo_threshold : -1.0f));
   const bool ready = tensor && sink_filled;
   if (ready && h->has_prev && !h->carry_tc_valid)
     // the previous batch ran on the exact matcher: convert the carried fp32 descriptors into the carry slot

@@ -37,7 +37,16 @@ struct MatchProblem {
   const float* t;  // [M,256]
   int N, M;
   int a_op, b_op;  // operand slots of q / t in the tensor matcher's bf16 workspace (match_tc.cu)
+  // optional row-band mask (the north star's "stereo row-band constraint" as a matcher mask): train row j is a
+  // candidate of query i iff |qy[i * ystride] - ty[j * ystride]| <= band.  qy == NULL: no mask.
+  const float* qy;
+  const float* ty;
+  int ystride;
+  float band;
 };
+__device__ __forceinline__ bool band_allowed(const MatchProblem& pr, int i, int j) {
+  return !pr.qy || fabsf(__fsub_rn(__ldg(pr.qy + (size_t)i * pr.ystride), __ldg(pr.ty + (size_t)j * pr.ystride))) <= pr.band;
+}
 
 // Where k_desc_normalize additionally writes each image's descriptors for the tensor matcher
 // (bf16 rows + fp32 squared norms + per-slot max norm), so the stereo pipeline needs no k_tc_prep.
@@ -96,12 +105,14 @@ void tc_workspace_free(Handle* h);
 cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* desc_base, const int* n_rows,
                                   int slot_stride_rows, const int* q_slot, const int* t_slot, int P);
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
-                                         int F, int K, int carry_slot);
+                                         int F, int K, int carry_slot, const spvo_keypoint* kpts, float band);
 // quads == nullptr: only the copies of `cl` run
 cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* matches, const int* n_matches,
                                const int* q2t, const uint8_t* keep, const int* carry_map, spvo_quad* quads,
                                int* n_quads, const CopyList& cl);
-cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M);
+cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M,
+                               const spvo_keypoint* q_kpts = nullptr, const spvo_keypoint* t_kpts = nullptr,
+                               float band = -1.0f);
 cudaError_t launch_stereo_filter(Handle* h, const spvo_keypoint* kpts_base, int slot_stride_rows,
                                  const int* q_slot, const int* t_slot, int P, int max_rows,
                                  const spvo_dmatch* matches, const int* n_matches, float stereo_threshold,
@@ -151,6 +162,7 @@ struct Handle {
   spvo_dmatch* st_matches = nullptr;
   int* st_q2t = nullptr;
   int* st_nm = nullptr;
+  spvo_keypoint* st_mkp = nullptr;  // [2 * st_rows] keypoints of a host-form masked match
   size_t st_rows = 0;
   // stereo stream state: previous batch's last left image
   float* carry_desc = nullptr;      // [max_k, 256]

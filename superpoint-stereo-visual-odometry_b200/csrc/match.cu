@@ -110,6 +110,7 @@ k_row_select(const MatchProblem* __restrict__ probs, const float* __restrict__ d
   float b0 = INFINITY, b1 = INFINITY;
   int x0 = INT_MAX, x1 = INT_MAX;
   for (int j = lane; j < pr.M; j += 32) {
+    if (!band_allowed(pr, i, j)) continue;
     const float d = Drow[j];
     if (lex_less(d, j, b0, x0)) {
       b1 = b0; x1 = x0; b0 = d; x0 = j;
@@ -154,6 +155,7 @@ k_col_select(const MatchProblem* __restrict__ probs, const float* __restrict__ d
   int x0 = INT_MAX;
   if (j < pr.M)
     for (int i = ty; i < pr.N; i += 8) {
+      if (!band_allowed(pr, i, j)) continue;
       const float d = D[(size_t)i * max_cols + j];
       if (lex_less(d, i, b0, x0)) { b0 = d; x0 = i; }
     }
@@ -194,7 +196,8 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
       d0 = row_d[o];
       keep = tr >= 0;
       if (keep && mode == SPVO_MATCH_NN_CROSSCHECK) keep = col_best[(size_t)p * max_cols + tr] == i;
-      if (keep && mode == SPVO_MATCH_KNN_RATIO) keep = d0 < __fmul_rn(ratio, row_d[o + 1]);
+      // (a masked row may have a single allowed train row although M >= 2: no second neighbour, no match)
+      if (keep && mode == SPVO_MATCH_KNN_RATIO) keep = row_best[o + 1] >= 0 && d0 < __fmul_rn(ratio, row_d[o + 1]);
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_warp[warp] = __popc(m);
@@ -239,17 +242,30 @@ __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, co
   pr.M = n_rows[ts];
   pr.a_op = 2 * p;
   pr.b_op = 2 * p + 1;
+  pr.qy = pr.ty = nullptr;
+  pr.ystride = 0;
+  pr.band = -1.0f;
   probs[p] = pr;
 }
 
 // Stereo stream problems: p < F stereo (left_f vs right_f); p >= F temporal (left_f vs left_{f-1},
 // or the carried last-left of the previous batch for f = 0; carry_n = 0 means "no previous frame").
 __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_out, const int* n_out,
-                                        const float* carry_desc, const int* carry_n, int F, int K, int carry_slot) {
+                                        const float* carry_desc, const int* carry_n, int F, int K, int carry_slot,
+                                        const spvo_keypoint* kpts, float band) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= 2 * F) return;
   MatchProblem pr;
+  pr.qy = pr.ty = nullptr;
+  pr.ystride = 0;
+  pr.band = -1.0f;
   if (p < F) {
+    if (kpts && band >= 0.0f) {  // masked mode: only the L<->R problems carry the row band
+      pr.qy = &kpts[(size_t)(2 * p) * K].y;
+      pr.ty = &kpts[(size_t)(2 * p + 1) * K].y;
+      pr.ystride = (int)(sizeof(spvo_keypoint) / sizeof(float));
+      pr.band = band;
+    }
     pr.q = desc_out + (size_t)(2 * p) * K * kD;
     pr.t = desc_out + (size_t)(2 * p + 1) * K * kD;
     pr.N = n_out[2 * p];
@@ -274,10 +290,16 @@ __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_o
   probs[p] = pr;
 }
 
-__global__ void k_set_problem(MatchProblem* probs, const float* q, int N, const float* t, int M) {
+__global__ void k_set_problem(MatchProblem* probs, const float* q, int N, const float* t, int M,
+                              const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band) {
   MatchProblem pr;
   pr.q = q; pr.t = t; pr.N = N; pr.M = M;
   pr.a_op = 0; pr.b_op = 1;
+  const bool masked = q_kpts && t_kpts && band >= 0.0f;
+  pr.qy = masked ? &q_kpts[0].y : nullptr;
+  pr.ty = masked ? &t_kpts[0].y : nullptr;
+  pr.ystride = (int)(sizeof(spvo_keypoint) / sizeof(float));
+  pr.band = band;
   probs[0] = pr;
 }
 
@@ -446,12 +468,12 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
 }
 
 cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const float* desc_out, const int* n_out,
-                                         int F, int K, int carry_slot) {
+                                         int F, int K, int carry_slot, const spvo_keypoint* kpts, float band) {
   if (F == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
     k_setup_stereo_problems<<<(2 * F + 127) / 128, 128, 0, h->stream>>>(probs, desc_out, n_out, h->carry_desc,
-                                                                       h->carry_n, F, K, carry_slot);
+                                                                       h->carry_n, F, K, carry_slot, kpts, band);
   }
   return cudaGetLastError();
 }
@@ -467,10 +489,11 @@ cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* match
   return cudaGetLastError();
 }
 
-cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M) {
+cudaError_t launch_set_problem(Handle* h, MatchProblem* probs, const float* q, int N, const float* t, int M,
+                               const spvo_keypoint* q_kpts, const spvo_keypoint* t_kpts, float band) {
   {
     LaunchScope ls(h, KID_SETUP);
-    k_set_problem<<<1, 1, 0, h->stream>>>(probs, q, N, t, M);
+    k_set_problem<<<1, 1, 0, h->stream>>>(probs, q, N, t, M, q_kpts, t_kpts, band);
   }
   return cudaGetLastError();
 }

@@ -261,6 +261,7 @@ constexpr float kOffUnit = 3.25f;        // unit-norm operands: v = |x|^2 - 2 S 
 struct __align__(16) TcShared {
   float nrm[kNormRing][kBN];
   uint2 colstage[2][2][4][kBN / 2];  // [tile parity][half][quadrant][column in half] -> (k0, k1) of 32 rows
+  float ytile[2][kBN];               // [tile parity][column]: the columns' keypoint rows (row-band mask only)
   uint64_t a_full[kNumKB], a_empty;
   uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % kNormRing
   uint64_t b_full[kBSlots], b_empty[kBSlots];
@@ -368,6 +369,10 @@ __device__ __forceinline__ u64k umax64(u64k a, u64k b) { return a < b ? b : a; }
 struct TcItem {
   int p, rb, Na, Nb, a_op, b_op, nct;
   bool valid;
+  const float* qy;
+  const float* ty;
+  int ystride;
+  float band;
 };
 __device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs, int w, int nrb) {
   TcItem it;
@@ -380,10 +385,14 @@ __device__ __forceinline__ TcItem tc_item(const MatchProblem* __restrict__ probs
   it.b_op = pr.b_op;
   it.nct = (it.Nb + kBN - 1) / kBN;
   it.valid = it.rb * kBM < it.Na && it.nct > 0;
+  it.qy = pr.qy;
+  it.ty = pr.ty;
+  it.ystride = pr.ystride;
+  it.band = pr.qy ? pr.band : INFINITY;  // unmasked problems of a masked launch: everything is allowed
   return it;
 }
 
-template <bool kUnit, bool kCols>
+template <bool kUnit, bool kCols, bool kMask>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs,
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, RowRec* __restrict__ row_rec,
@@ -521,6 +530,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           ca[m] = __fmaf_rn(na, sc.sc, sc.off);
         }
       }
+      float yi[4] = {0.f, 0.f, 0.f, 0.f};  // keypoint rows (image y) of this thread's four rows: row-band mask
+      if (kMask && it.qy) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int row = it.rb * kBM + (int)rid[m];
+          if (row < it.Na) yi[m] = __ldg(it.qy + (size_t)row * it.ystride);
+        }
+      }
       if (kCols) {  // start the next valid item's norm loads now: they land long before that item begins
         pf_w = -1;
         for (int w2 = w + gridDim.x; w2 < n_items; w2 += gridDim.x) {
@@ -547,6 +564,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
         tc_fence_after();
         // the tile's column norms were bulk-copied to shared memory next to its B operand
         mbar_wait(smem_u32(&sh->nrm_full[gt % kNormRing]), (gt / kNormRing) & 1);
+        if (kMask) {  // the 256 epilogue threads stage the tile's 256 column keypoint rows (two buffers by tile parity)
+          const int cidx = (int)threadIdx.x - 64, col = ct * kBN + cidx;
+          sh->ytile[gt & 1][cidx] = (it.ty && col < it.Nb) ? __ldg(it.ty + (size_t)col * it.ystride) : 0.f;
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
         uint32_t k0[4], k1[4];  // tile-local row lists (id = 16 hh + 2 n + e: this thread's column within the tile half)
 #pragma unroll
         for (int m = 0; m < 4; ++m) k0[m] = k1[m] = 0xFFFFFFFFu;
@@ -564,6 +586,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
             cb[2 * n] = __fmaf_rn(nb.x, sr.sc, sr.off);
             cb[2 * n + 1] = __fmaf_rn(nb.y, sr.sc, sr.off);
           }
+          float yc[16];
+          if (kMask) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              const float2 y2 = *reinterpret_cast<const float2*>(&sh->ytile[gt & 1][cbase + 8 * n + 2 * q]);
+              yc[2 * n] = y2.x;
+              yc[2 * n + 1] = y2.y;
+            }
+          }
           tmem_ld_wait();
           if (hh == 1) {
             tc_fence_before();
@@ -578,12 +609,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
               const float s0 = __uint_as_float(acc[m >> 1][4 * n + 2 * (m & 1)]);
               const float s1 = __uint_as_float(acc[m >> 1][4 * n + 2 * (m & 1) + 1]);
               // row direction: one IMAD packs value and column id; padded columns carry a NaN norm -> key 0xFFFFFFxx
-              const uint32_t ka = __float_as_uint(__fmaf_rn(s0, sr.m2sc, cb[2 * n])) * r256 + (uint32_t)(16 * hh + 2 * n);
-              const uint32_t kb = __float_as_uint(__fmaf_rn(s1, sr.m2sc, cb[2 * n + 1])) * r256 + (uint32_t)(16 * hh + 2 * n + 1);
+              uint32_t ka = __float_as_uint(__fmaf_rn(s0, sr.m2sc, cb[2 * n])) * r256 + (uint32_t)(16 * hh + 2 * n);
+              uint32_t kb = __float_as_uint(__fmaf_rn(s1, sr.m2sc, cb[2 * n + 1])) * r256 + (uint32_t)(16 * hh + 2 * n + 1);
+              // row-band mask: a pair outside the band is nobody's candidate, in either direction
+              const bool ok0 = !kMask || fabsf(__fsub_rn(yi[m], yc[2 * n])) <= it.band;
+              const bool ok1 = !kMask || fabsf(__fsub_rn(yi[m], yc[2 * n + 1])) <= it.band;
+              if (kMask) {
+                ka = ok0 ? ka : 0xFFFFFFFFu;
+                kb = ok1 ? kb : 0xFFFFFFFFu;
+              }
               push_two(k0[m], k1[m], ka, kb);
               if (kCols) {
                 ck[m][0] = __float_as_uint(__fmaf_rn(s0, sc.m2sc, ca[m])) * 256u + rid[m];
                 ck[m][1] = __float_as_uint(__fmaf_rn(s1, sc.m2sc, ca[m])) * 256u + rid[m];
+                if (kMask) {
+                  ck[m][0] = ok0 ? ck[m][0] : 0xFFFFFFFFu;
+                  ck[m][1] = ok1 ? ck[m][1] : 0xFFFFFFFFu;
+                }
               }
             }
             if (kCols) {
@@ -999,6 +1041,9 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
       a[r][0] = x.x; a[r][1] = x.y; a[r][2] = x.z; a[r][3] = x.w;
       a[r][4] = y.x; a[r][5] = y.y; a[r][6] = y.z; a[r][7] = y.w;
     }
+    // row-band mask: this lane finishes row myr of the group (query index for the forward direction)
+    const int my_i = fb_list[(size_t)dp * cap + r0 + min(myr, nr - 1)];
+    auto allowed = [&](int row, int col) { return rev ? band_allowed(pr, col, row) : band_allowed(pr, row, col); };
     float v[3] = {INFINITY, INFINITY, INFINITY};
     int ix[3] = {-1, -1, -1};
     constexpr int kU = 2;  // columns per step; the next step's loads are issued before this step's math
@@ -1052,7 +1097,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         }
         q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
         q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-        if (j < Nb) {
+        if (j < Nb && allowed(my_i, j)) {
           const float g = __fmaf_rn(-2.0f, q1, nbs[u]);
           if (g < v[2]) {
             if (g < v[1]) {
@@ -1113,7 +1158,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
         for (int j = half; j < Nb + half; j += 2) {
           const int jj = j < Nb ? j : Nb - 1;
           const float d = exact_dist_half(arow, B + (size_t)jj * kDim, l16);
-          if (j < Nb) top2_push(d, j, b0, x0, b1, x1);
+          if (j < Nb && allowed(i, j)) top2_push(d, j, b0, x0, b1, x1);
         }
         if (lane == 0) atomicAdd(&counters[2], 1ull);
       } else {
@@ -1340,8 +1385,11 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
     const int unit = (operands_ready && w->fp16) ? 1 : 0;
     const size_t smem = 1024 + (size_t)kNumKB * kTileBytes + (size_t)kBSlots * kBSlotBytes + sizeof(TcShared);
     {
-      auto kern = cross ? (unit ? k_tc_gemm<true, true> : k_tc_gemm<false, true>)
-                        : (unit ? k_tc_gemm<true, false> : k_tc_gemm<false, false>);
+      const bool mask = (cfg.flags & SPVO_MATCH_FLAG_ROW_BAND) != 0;  // some problem carries a row-band mask
+      auto kern = mask ? (cross ? (unit ? k_tc_gemm<true, true, true> : k_tc_gemm<false, true, true>)
+                                : (unit ? k_tc_gemm<true, false, true> : k_tc_gemm<false, false, true>))
+                       : (cross ? (unit ? k_tc_gemm<true, true, false> : k_tc_gemm<false, true, false>)
+                                : (unit ? k_tc_gemm<true, false, false> : k_tc_gemm<false, false, false>));
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       LaunchScope ls(h, KID_TC_GEMM);
       const int n_items = (cap / kBM) * P;  // ONE Gram matrix per problem: both directions come from its epilogue

@@ -156,8 +156,10 @@ class Frontend:
                        _ptr(n_out), _ptr(scores_out)))
 
     # ---- match --------------------------------------------------------------------------------
-    def match(self, q: np.ndarray, t: np.ndarray, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO):
-        """Host-buffer match (spvo_match).  Returns (DMatch structured array, q2t map)."""
+    def match(self, q: np.ndarray, t: np.ndarray, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
+              q_kpts=None, t_kpts=None, band=None):
+        """Host-buffer match (spvo_match; spvo_match_masked when q_kpts / t_kpts / band give a row-band mask).
+        Returns (DMatch structured array, q2t map)."""
         q = np.ascontiguousarray(q, np.float32).reshape(-1, 256)
         t = np.ascontiguousarray(t, np.float32).reshape(-1, 256)
         N, M = q.shape[0], t.shape[0]
@@ -165,8 +167,15 @@ class Frontend:
         q2t = np.full(max(N, 1), -1, np.int32)
         n = C.c_int(0)
         cfg = MatchCfg(mode, ratio, algorithm, 0)
-        self._check(self._L.spvo_match(self._h, _ptr(q), N, _ptr(t), M, 256, C.byref(cfg), _ptr(out), C.addressof(n),
-                                       _ptr(q2t)))
+        if band is None:
+            self._check(self._L.spvo_match(self._h, _ptr(q), N, _ptr(t), M, 256, C.byref(cfg), _ptr(out),
+                                           C.addressof(n), _ptr(q2t)))
+        else:
+            qk = np.ascontiguousarray(q_kpts, KEYPOINT_DTYPE)
+            tk = np.ascontiguousarray(t_kpts, KEYPOINT_DTYPE)
+            assert len(qk) == N and len(tk) == M
+            self._check(self._L.spvo_match_masked(self._h, _ptr(q), N, _ptr(t), M, 256, C.byref(cfg), _ptr(qk), _ptr(tk),
+                                                  float(band), _ptr(out), C.addressof(n), _ptr(q2t)))
         return out[: n.value].copy(), q2t[:N].copy()
 
     def match_device(self, q, N, t, M, out, n_matches, q2t=None, mode=MATCH_NN_CROSSCHECK, ratio=0.8,
@@ -199,17 +208,19 @@ class Frontend:
 
     @staticmethod
     def _stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
-                    stereo_threshold, min_disparity):
+                    stereo_threshold, min_disparity, row_band=False):
         return _lib.StereoCfg(DecodeCfg(conf_thresh, dist_thresh, border_remove, int(max_keypoints)),
-                              MatchCfg(mode, ratio, algorithm, 0), stereo_threshold, min_disparity)
+                              MatchCfg(mode, ratio, algorithm, _lib.MATCH_FLAG_ROW_BAND if row_band else 0),
+                              stereo_threshold, min_disparity)
 
     def stereo_batch_device(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
                             max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
-                            stereo_threshold=2.0, min_disparity=0.25, f16=False):
+                            stereo_threshold=2.0, min_disparity=0.25, f16=False, row_band=False):
         """spvo_stereo_batch_device[_f16].  `out` maps the spvo_stereo_out field names to CUDA tensors; f16=True:
-        semi / desc are float16 tensors (an fp16 engine's output bindings)."""
+        semi / desc are float16 tensors (an fp16 engine's output bindings); row_band=True: the L<->R matching runs
+        under the row-band mask |y_l - y_r| <= stereo_threshold (SPVO_MATCH_FLAG_ROW_BAND)."""
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
-                               stereo_threshold, min_disparity)
+                               stereo_threshold, min_disparity, row_band)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
                               ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
         fn = self._L.spvo_stereo_batch_device_f16 if f16 else self._L.spvo_stereo_batch_device
@@ -217,10 +228,10 @@ class Frontend:
 
     def stereo_batch(self, semi, desc, F, H, W, out: dict, conf_thresh=0.015, dist_thresh=4, border_remove=4,
                      max_keypoints=1000, mode=MATCH_NN_CROSSCHECK, ratio=0.8, algorithm=MATCHER_AUTO,
-                     stereo_threshold=2.0, min_disparity=0.25, f16=False):
+                     stereo_threshold=2.0, min_disparity=0.25, f16=False, row_band=False):
         """spvo_stereo_batch[_f16] (host pointers: numpy arrays or pinned CPU torch tensors); synchronous."""
         cfg = self._stereo_cfg(conf_thresh, dist_thresh, border_remove, max_keypoints, mode, ratio, algorithm,
-                               stereo_threshold, min_disparity)
+                               stereo_threshold, min_disparity, row_band)
         so = _lib.StereoOut(*[_ptr(out.get(k)) for k in
                               ("kpts", "desc", "n_kpts", "matches", "n_matches", "q2t", "stereo_keep", "quads", "n_quads")])
         fn = self._L.spvo_stereo_batch_f16 if f16 else self._L.spvo_stereo_batch

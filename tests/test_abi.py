@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(spvo):
         assert hasattr(L, n), f"{n} declared in spvo_frontend.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding list and header disagree"
     hdr = open(os.path.join(ROOT, "include", "spvo_frontend.h")).read()
-    assert L.spvo_abi_version() == int(re.search(r"#define\s+SPVO_ABI_VERSION\s+(\d+)", hdr).group(1)) == 3
+    assert L.spvo_abi_version() == int(re.search(r"#define\s+SPVO_ABI_VERSION\s+(\d+)", hdr).group(1)) == 4
 
 
 def test_pod_layouts(spvo):

@@ -103,3 +103,44 @@ def test_stereo_filter(oracle):
     m["queryIdx"] = m["trainIdx"] = [0, 1, 2]
     keep = oracle.stereo_filter(kl, kr, m, 2.0, 0.25)   # BASE:169-172
     assert list(keep) == [True, False, False]
+
+
+def _cv2_masked(q, t, qy, ty, band, mode, ratio=0.8):
+    """The masked matching AS cv2 does it: two masked BFMatcher(NORM_L2, crossCheck=False) calls + a manual mutual test
+    (cv::BFMatcher rejects crossCheck with a mask), or knnMatch(k=2, mask) + the reference's ratio test."""
+    import cv2
+    mask = (np.abs(qy[:, None] - ty[None, :]) <= band).astype(np.uint8)
+    bf = cv2.BFMatcher(cv2.NORM_L2, False)
+    if mode == 2:
+        out = []
+        for m in bf.knnMatch(q, t, 2, mask=mask):
+            if len(m) == 2 and m[0].distance < np.float32(ratio) * np.float32(m[1].distance):
+                out.append((m[0].queryIdx, m[0].trainIdx, m[0].distance))
+        return out
+    fwd = bf.match(q, t, mask=mask)
+    if mode == 0:
+        return [(m.queryIdx, m.trainIdx, m.distance) for m in fwd]
+    rev = {m.queryIdx: m.trainIdx for m in bf.match(t, q, mask=np.ascontiguousarray(mask.T))}
+    return [(m.queryIdx, m.trainIdx, m.distance) for m in fwd if rev.get(m.trainIdx, -1) == m.queryIdx]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_masked_matching_equals_masked_cv2(oracle, mode):
+    """Row-band mask (north star): the oracle's masked matching is what masked cv2 calls give."""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import unit_rows
+    rng = np.random.default_rng(5)
+    for N, M, band in ((300, 280, 2.0), (64, 200, 0.5), (500, 500, 8.0), (40, 3, 1.0)):
+        q, t = unit_rows(N, seed=N), unit_rows(M, seed=M + 1)
+        t[: min(N, M) // 2] = q[: min(N, M) // 2] + 0.05 * rng.standard_normal((min(N, M) // 2, 256)).astype(np.float32)
+        qy = rng.integers(0, 60, N).astype(np.float32)
+        ty = (qy[rng.integers(0, N, M)] + rng.integers(-3, 4, M)).astype(np.float32)
+        want = _cv2_masked(q, t, qy, ty, band, mode)
+        got, q2t = oracle.match(q, t, mode=mode, qy=qy, ty=ty, band=band)
+        assert [(int(m["queryIdx"]), int(m["trainIdx"])) for m in got] == [(a, b) for a, b, _ in want]
+        assert [np.float32(m["distance"]).view(np.uint32) for m in got] == [np.float32(d).view(np.uint32) for _, _, d in want]
+        assert all(q2t[a] == b for a, b, _ in want) and (q2t >= 0).sum() == len(want)
+    # no mask arguments = the unmasked matcher
+    a, _ = oracle.match(q, t, mode=mode)
+    b, _ = oracle.match(q, t, mode=mode, qy=qy, ty=ty, band=-1.0)
+    assert a.tobytes() == b.tobytes()
