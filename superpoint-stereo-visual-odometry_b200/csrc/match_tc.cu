@@ -620,8 +620,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
               }
               push_two(k0[m], k1[m], ka, kb);
               if (kCols) {
-                ck[m][0] = __float_as_uint(__fmaf_rn(s0, sc.m2sc, ca[m])) * 256u + rid[m];
-                ck[m][1] = __float_as_uint(__fmaf_rn(s1, sc.m2sc, ca[m])) * 256u + rid[m];
+                // (run-time multiplier: with a literal 256 the compiler splits one row's packing into SHL + LOP3 on the ALU pipe)
+                ck[m][0] = __float_as_uint(__fmaf_rn(s0, sc.m2sc, ca[m])) * r256 + rid[m];
+                ck[m][1] = __float_as_uint(__fmaf_rn(s1, sc.m2sc, ca[m])) * r256 + rid[m];
                 if (kMask) {
                   ck[m][0] = ok0 ? ck[m][0] : 0xFFFFFFFFu;
                   ck[m][1] = ok1 ? ck[m][1] : 0xFFFFFFFFu;
