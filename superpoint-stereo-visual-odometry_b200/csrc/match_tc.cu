@@ -359,10 +359,6 @@ __device__ __forceinline__ void col_butterfly(uint32_t* k0, uint32_t* k1, bool u
   }
 }
 
-// 64-bit shortlist entry: (24-bit value << 32) | column; ~0 = none
-typedef unsigned long long u64k;
-__device__ __forceinline__ u64k umin64(u64k a, u64k b) { return a < b ? a : b; }
-__device__ __forceinline__ u64k umax64(u64k a, u64k b) { return a < b ? b : a; }
 // Work item = (problem p, 128-row block rb): A = the problem's queries, B = its train descriptors.  The kernel is
 // PERSISTENT: one CTA per SM walks items bid, bid + grid, ...; barriers and TMEM are set up once, and the B ring /
 // accumulator pipelines run continuously across items (global k-block and tile counters give slot and phase).
@@ -721,14 +717,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 // DMatch.distance is filled in later only if the match survives).  Everything else is queued, with its shortlist,
 // for the warp-per-row k_tc_rerank.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void top4_insert(u64k x, u64k& e0, u64k& e1, u64k& e2, u64k& e3) {
-  u64k t;
-  t = umin64(e0, x); x = umax64(e0, x); e0 = t;
-  t = umin64(e1, x); x = umax64(e1, x); e1 = t;
-  t = umin64(e2, x); x = umax64(e2, x); e2 = t;
-  e3 = umin64(e3, x);
-}
-
 __global__ void __launch_bounds__(256)
 k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm,
             const unsigned* __restrict__ opmax, const RowRec* __restrict__ row_rec, const ColRec* __restrict__ col_rec,
