@@ -69,9 +69,9 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA + T
 //   <= 2*256*2^-25 per unit of max|b_k| -> covered by kEpsAbs.
 constexpr float kEpsRelBf16 = 0.0085f, kEpsRelFp16 = 0.0022f, kEpsAbs = 1e-5f;
 // Key values live in [2, 8) after an affine map (tc_scale); their fp32 arithmetic (two fused multiply-adds, the
-// affine map and its inverse) is off by < 1e-6 per value in those units, and the row records keep 20 of the 24 value
-// bits (< 1.6e-5): kKeySlack covers a comparison of two.
-constexpr float kKeySlack = 4e-5f;
+// affine map and its inverse) is off by < 1e-6 per value in those units, and the triage keeps 19 of the 24 value
+// bits (rounded down, < 3.1e-5): kKeySlack covers a comparison of two.
+constexpr float kKeySlack = 6e-5f;
 // norm of a padded row / column: NaN, so that every key built from it is the canonical NaN 0x7FFFFFFF -> the largest
 // 24-bit key value (kNone24) -- padded entries never enter a shortlist
 __device__ __forceinline__ float pad_norm() { return __uint_as_float(0x7FFFFFFFu); }
@@ -736,8 +736,16 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
   if (Nb == 0) {
     resolved = true;
   } else {
-    // entries: (24-bit value << 32) | column; every value is widened to 24 bits (row records keep 20, rounded down)
-    u64k e0 = ~0ull, e1 = ~0ull, e2 = ~0ull, e3 = ~0ull;
+    // entries: 32-bit keys (19-bit value << 13) | column -- values rounded DOWN from the records' 20 / 24 bits (covered
+    // by kKeySlack); ~0 = none.  The bound stays 24-bit.
+    uint32_t e0 = ~0u, e1 = ~0u, e2 = ~0u, e3 = ~0u;
+    auto insert = [&](uint32_t x) {
+      uint32_t t;
+      t = min(e0, x); x = max(e0, x); e0 = t;
+      t = min(e1, x); x = max(e1, x); e1 = t;
+      t = min(e2, x); x = max(e2, x); e2 = t;
+      e3 = min(e3, x);
+    };
     uint32_t bound = kNone24;
     if (!rev) {
       const uint4* rec = reinterpret_cast<const uint4*>(row_rec + ((size_t)p * cap + i) * 8);
@@ -748,11 +756,10 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
         const uint32_t kk[2] = {r.x, r.y};
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
-          if ((kk[z] >> 12) < kNone20) {
-            const uint32_t id = kk[z] & 31u, tile = (kk[z] >> 5) & 31u;
-            const uint32_t col = tile * kBN + hf * 128 + (id >> 4) * 64 + ((id >> 1) & 7) * 8 + 2 * q + (id & 1);
-            top4_insert(((u64k)((kk[z] >> 12) << 4) << 32) | col, e0, e1, e2, e3);
-          }
+          const uint32_t id = kk[z] & 31u, tile = (kk[z] >> 5) & 31u;
+          const uint32_t col = tile * kBN + hf * 128 + (id >> 4) * 64 + ((id >> 1) & 7) * 8 + 2 * q + (id & 1);
+          // a "none" entry (value 0xFFFFF) stays the maximum of its 19-bit field: 0x7FFFF
+          insert(((kk[z] >> 13) << 13) | col);
         }
         if (r.z < kNone20) bound = min(bound, r.z << 4);
       }
@@ -760,22 +767,23 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
       const int nrb = cap / kBM, nrbv = (pr.N + kBM - 1) / kBM;  // row blocks of the forward problem that exist
       for (int rb = 0; rb < nrbv; ++rb) {
         const uint4 c = __ldg(reinterpret_cast<const uint4*>(col_rec + ((size_t)p * nrb + rb) * cap + i));
-        if ((c.x >> 8) < kNone24) top4_insert(((u64k)(c.x >> 8) << 32) | (uint32_t)(rb * kBM + (c.x & 0xFFu)), e0, e1, e2, e3);
-        if ((c.y >> 8) < kNone24) top4_insert(((u64k)(c.y >> 8) << 32) | (uint32_t)(rb * kBM + (c.y & 0xFFu)), e0, e1, e2, e3);
+        insert(((c.x >> 13) << 13) | (uint32_t)(rb * kBM + (c.x & 0xFFu)));
+        insert(((c.y >> 13) << 13) | (uint32_t)(rb * kBM + (c.y & 0xFFu)));
         bound = min(bound, min(kNone24, c.z));  // rows of this block beyond its two listed ones
       }
     }
-    bound = min(bound, (uint32_t)min((u64k)kNone24, e3 >> 32));  // listed, but beyond the three kept
-    if (Nb <= kTop) bound = kNone24;                              // the list is the whole row
+    constexpr uint32_t kNone19 = 0x7FFFFu;
+    if ((e3 >> 13) < kNone19) bound = min(bound, (e3 >> 13) << 5);  // listed, but beyond the three kept
+    if (Nb <= kTop) bound = kNone24;                                // the list is the whole row
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const TcScale ts = tc_scale(bmax, amax, unit != 0);  // the reduction ran over the B side's norms
     const float inv = 1.0f / ts.sc;
-    const u64k ee[3] = {e0, e1, e2};
+    const uint32_t ee[3] = {e0, e1, e2};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const bool ok = ee[k] != ~0ull;
-      sl.g[k] = ok ? (key_value((uint32_t)(ee[k] >> 32)) - ts.off) * inv : INFINITY;
-      sl.j[k] = ok ? (int)(uint32_t)ee[k] : -1;
+      const bool ok = (ee[k] >> 13) < kNone19;
+      sl.g[k] = ok ? (key_value((ee[k] >> 13) << 5) - ts.off) * inv : INFINITY;
+      sl.j[k] = ok ? (int)(ee[k] & 0x1FFFu) : -1;
     }
     sl.bound = bound < kNone24 ? (key_value(bound) - ts.off) * inv : INFINITY;
     sl.pad = 0;
