@@ -264,6 +264,7 @@ struct __align__(16) TcShared {
   float ytile[2][kBN];               // [tile parity][column]: the columns' keypoint rows (row-band mask only)
   uint64_t a_full[kNumKB], a_empty;
   uint64_t nrm_full[kNormRing];  // column norms of tile gt landed in slot gt % kNormRing
+  uint64_t nrm_empty[kNormRing]; // ... and every epilogue warp has read them (explicit edge for the slot's reuse by tile gt+4)
   uint64_t b_full[kBSlots], b_empty[kBSlots];
   uint64_t acc_full[kAccStages], acc_empty[kAccStages];
   uint32_t tmem_base;
@@ -406,7 +407,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < kNumKB; ++kb) mbar_init(smem_u32(&sh->a_full[kb]), 1);
     mbar_init(smem_u32(&sh->a_empty), 1);
-    for (int s = 0; s < kNormRing; ++s) mbar_init(smem_u32(&sh->nrm_full[s]), 1);
+    for (int s = 0; s < kNormRing; ++s) {
+      mbar_init(smem_u32(&sh->nrm_full[s]), 1);
+      mbar_init(smem_u32(&sh->nrm_empty[s]), kEpiWarps);
+    }
     for (int s = 0; s < kBSlots; ++s) {
       mbar_init(smem_u32(&sh->b_full[s]), 1);
       mbar_init(smem_u32(&sh->b_empty[s]), 1);
@@ -450,9 +454,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           if (ct == 1) load_a();
           const int b_row = it.b_op * cap + ct * kBN;
           // the tile's 256 column norms: 1-D bulk copy into slot gt % 4 with its own mbarrier (the epilogue waits
-          // on it directly).  The slot is rewritten by tile gt+4, whose first k-block reuses the ring slot last
-          // read by the MMAs of tile gt+3, which waited for the epilogue to drain tile gt+1 -- and a warp drains
-          // tile gt+1 only after it has finished the arithmetic (and norm reads) of tile gt: no overwrite race.
+          // on it directly).  The slot is rewritten by tile gt+4; the epilogue warps signal nrm_empty when they
+          // have read tile gt's norms (the B ring / accumulator chain orders this transitively as well).
           const uint32_t nb_bar = smem_u32(&sh->nrm_full[gt % kNormRing]);
           for (int kb = 0; kb < kNumKB; ++kb, ++gk) {
             const int s = gk % kBSlots, ph = (gk / kBSlots) & 1;
@@ -462,6 +465,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
               tma_load_2d(sB + s * kBSlotBytes + hb * kTileBytes, &tmap, smem_u32(&sh->b_full[s]), kb * kKB,
                           b_row + hb * kBM);
             if (kb == 0) {
+              mbar_wait(smem_u32(&sh->nrm_empty[gt % kNormRing]), ((gt / kNormRing) & 1) ^ 1);  // tile gt-4's norms are read
               mbar_expect_tx(nb_bar, kBN * 4);
               bulk_load_1d(smem_u32(&sh->nrm[gt % kNormRing][0]), nrm + (size_t)b_row, kBN * 4, nb_bar);
             }
@@ -595,6 +599,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
           if (hh == 1) {
             tc_fence_before();
             epi_release(smem_u32(&sh->acc_empty[sa]), lane);  // accumulator is in registers: release it to the MMA warp
+            if (lane == 0) mbar_arrive(smem_u32(&sh->nrm_empty[gt % kNormRing]));  // (after the __syncwarp above) norms consumed
           }
           uint32_t c0[16], c1[16];  // column lists over this thread's four rows
 #pragma unroll
@@ -1025,6 +1030,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
   const int myr = lane >> 2;        // after the butterfly, lanes 4r..4r+3 hold row r's dot product
   float* rv = cluster.map_shared_rank(&s_v[0][0][0], 0);
   int* rj = cluster.map_shared_rank(&s_j[0][0][0], 0);
+  cluster.sync();  // rank 0 must be resident before anybody writes into its shared memory
 
   for (int r0 = 0; r0 < nfb; r0 += kFbRows) {
     const int nr = min(kFbRows, nfb - r0);
