@@ -100,6 +100,8 @@ int spvo_create(spvo_handle* out, int device, int max_batch, int max_height, int
   }
   h->stream = h->own_stream;
   ALLOC(h->heat, (size_t)max_batch * px * sizeof(float));
+  ALLOC(h->spill_thr, (size_t)max_batch * sizeof(uint32_t));
+  cudaMemset(h->spill_thr, 0x7F, (size_t)max_batch * sizeof(uint32_t));  // no history yet: nothing is stored
   ALLOC(h->cand_list, (size_t)max_batch * decode_list_bytes_per_image());
   ALLOC(h->cellmax, (size_t)max_batch * cells * sizeof(uint2));
   ALLOC(h->nms_bitmap, (size_t)max_batch * (px / 16 + 64) * sizeof(unsigned));  // H*ceil(W/32) <= H*W/16 for W >= 16
@@ -127,7 +129,7 @@ int spvo_destroy(spvo_handle hh) {
   DeviceGuard g(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   tc_workspace_free(h);
-  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->cand_list, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
+  void* ptrs[] = {h->pp_src, h->pp_dst_f, h->pp_dst_u8, h->pp_tab, h->nms_bitmap, h->cellmax, h->desc_tmp, h->kp_par, h->heat, h->spill_thr, h->cand_list, h->counters, h->st_semi, h->st_desc, h->st_kpts, h->st_desc_out, h->st_n,
                   h->st_scores, h->dist, h->row_best, h->row_d, h->col_best, h->probs, h->st_q, h->st_t,
                   h->st_matches, h->st_q2t, h->st_nm, h->st_mkp, h->carry_desc, h->carry_kpts, h->carry_n, h->carry_map, h->st_quads, h->st_nquads,
                   h->st_smatches, h->st_snm, h->st_sq2t, h->st_skeep};

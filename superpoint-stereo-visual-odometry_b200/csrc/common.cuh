@@ -125,8 +125,9 @@ struct Handle {
   cudaStream_t stream = nullptr;
   int max_batch = 0, max_h = 0, max_w = 0, max_k = 0;
   // decode workspace
-  float* heat = nullptr;          // [max_batch, max_h*max_w]
   unsigned long long* cand_list = nullptr;  // [max_batch, kListCap] candidate keys of k_detect's current generation
+  float* heat = nullptr;          // [max_batch, max_h*max_w] heat values of the cells k_softmax_heat stores (sparse)
+  uint32_t* spill_thr = nullptr;  // [max_batch] per image slot: storing threshold for the next decode call
   uint2* cellmax = nullptr;       // [max_batch, cells] per-cell (max, second max | argmax) records of the heatmap
   unsigned* nms_bitmap = nullptr; // [max_batch, max_h*ceil(max_w/32)] suppression bitmap of the multi-chunk path
   float* desc_tmp = nullptr;      // [max_batch, 256, max_k] un-normalised descriptor values (k_desc_planes)
@@ -261,6 +262,58 @@ __device__ __forceinline__ float spvo_exp(float x0) {
   int e = (int)m + 127;
   float scale = __uint_as_float((uint32_t)e << 23);
   return fmaxf(__fmul_rn(y, scale), x0);
+}
+
+// Two spvo_exp at once on Blackwell's packed fp32 pipe (fma / mul / add .rn.f32x2: one issue slot for two IEEE
+// operations, each lane rounded exactly like the scalar instruction).  The clamp, floor, float -> int and the final
+// max have no packed form and stay scalar.  Same value sequence as spvo_exp, bit for bit.  Measured on B200 in
+// k_softmax_heat: a packed instruction occupies the FMA pipe for about four issue cycles (two scalar FFMAs take two),
+// so packing trades FMA-pipe time for issue slots -- worth it only where issue is the tighter bound.
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void spvo_exp_x2(float xa0, float xb0, float& ea, float& eb) {
+  const float xa = fminf(fmaxf(xa0, -88.3762626647949f), 88.3762626647950f);
+  const float xb = fminf(fmaxf(xb0, -88.3762626647949f), 88.3762626647950f);
+  const unsigned long long x = f32x2_pack(xa, xb);
+  float ta, tb;
+  f32x2_unpack(f32x2_fma(x, f32x2_pack(1.44269504088896341f, 1.44269504088896341f), f32x2_pack(0.5f, 0.5f)), ta, tb);
+  const float ma = floorf(ta), mb = floorf(tb);
+  const unsigned long long r = f32x2_fma(f32x2_pack(ma, mb), f32x2_pack(-0.6931471805599453f, -0.6931471805599453f), x);
+  const unsigned long long r2 = f32x2_mul(r, r);
+  unsigned long long y = f32x2_pack(1.9875691500E-4f, 1.9875691500E-4f);
+  y = f32x2_fma(y, r, f32x2_pack(1.3981999507E-3f, 1.3981999507E-3f));
+  y = f32x2_fma(y, r, f32x2_pack(8.3334519073E-3f, 8.3334519073E-3f));
+  y = f32x2_fma(y, r, f32x2_pack(4.1665795894E-2f, 4.1665795894E-2f));
+  y = f32x2_fma(y, r, f32x2_pack(1.6666665459E-1f, 1.6666665459E-1f));
+  y = f32x2_fma(y, r, f32x2_pack(5.0000001201E-1f, 5.0000001201E-1f));
+  y = f32x2_fma(y, r2, r);
+  y = f32x2_add(y, f32x2_pack(1.0f, 1.0f));
+  const float sa = __uint_as_float((uint32_t)((int)ma + 127) << 23), sb = __uint_as_float((uint32_t)((int)mb + 127) << 23);
+  float pa, pb;
+  f32x2_unpack(f32x2_mul(y, f32x2_pack(sa, sb)), pa, pb);
+  ea = fmaxf(pa, xa0);
+  eb = fmaxf(pb, xb0);
 }
 
 }  // namespace spvo

@@ -13,6 +13,7 @@
 //
 // HBM-bound integer/float streaming work: coalesced 128 B channel-plane reads of semi, 32 B-aligned
 // float4 heatmap stores, warp-shuffle reductions; no tensor cores here.
+#include <cstring>
 #include <stdlib.h>
 
 #include <cuda_bf16.h>
@@ -30,13 +31,19 @@ __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
 // ------------------------------------------------------------------------------------------------
-// K1: softmax + heatmap.  One THREAD per 8x8 cell, 128 consecutive cells per block.
-//   * every global load is one 128 B coalesced request per warp (a channel plane, 32 consecutive cells); all 65
-//     loads of a thread are independent, so a warp keeps up to 8 KB in flight;
+// K1: softmax, reduced to one RECORD per 8x8 cell.  One THREAD per cell, 128 consecutive cells per block.
+//   * every global load is one 128 B coalesced request per warp (a channel plane, 32 consecutive cells); the loads
+//     of a thread are independent, so a warp keeps several KB in flight;
 //   * the 65-term channel sum must be accumulated in channel order (oracle: s = s + e_c, c = 0..64): it is a
 //     plain sequential chain inside the thread -- no shared memory, no barriers;
-//   * channel c is pixel (c / 8, c % 8) of the cell: per heatmap row a warp stores 32 cells x 32 B = 1 KB
-//     contiguous.
+//   * the heatmap itself (NN:266-326: p_c = e_c / (sum + 1e-5), channel c = pixel (c / 8, c % 8) of the cell) is not
+//     an output of the path, and k_detect only ever needs the pixels of the cells that hold two or more candidates.
+//     A cell's record is its largest and second largest heat value: RN(e / denom) is monotone in e, so they are the
+//     quotients of the two largest exponentials -- two divisions per cell instead of 64.  The 64 heat values are
+//     stored only for cells whose second value reaches a per-image-slot threshold that k_detect left behind on its
+//     previous call (0.9 x the lowest score bound its walk needed): a PREDICTION of the cells it will open.  A
+//     wrong prediction costs time, never correctness: k_detect recomputes any unstored cell it needs from the
+//     logits (visit_cells, same arithmetic), 65 scattered sectors instead of 8.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHeatThreads = 128;
 
@@ -53,59 +60,113 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
   return __fmaf_rn(__fmaf_rn(-q1, b, a), y, q1);
 }
 
+// Is a cell's 8x8 block of heat values stored ("spilled") by k_softmax_heat?  rec_y = the record's second word;
+// both kernels evaluate exactly this predicate with the same per-image threshold.
+__device__ __forceinline__ bool cell_spilled(uint32_t rec_y, uint32_t thr_bits, uint32_t conf_bits) {
+  const uint32_t sb = rec_y | 63u;  // upper bound of the second largest pixel
+  return sb >= thr_bits && sb > conf_bits;
+}
+
+// Heat values of the marked cells of a warp (bit l of `marked`: lane l's cell), kLanes lanes per cell, 64 / kLanes
+// consecutive pixels each.  cell / denom: each lane's own cell index and softmax denominator.
+template <int kLanes, typename T>
+__device__ __forceinline__ void store_heat_cells(unsigned marked, const T* __restrict__ img, float* __restrict__ heat_img,
+                                                 int cell, float denom, int cells, int Wc, int fast_div) {
+  constexpr int kPer = 64 / kLanes;      // pixels per lane: 2 (a quarter of a heat row) or 8 (a heat row)
+  constexpr int kGroups = 32 / kLanes;   // cells per round
+  const int lane = threadIdx.x & 31, grp = lane / kLanes, sub = lane % kLanes;
+  const int W = Wc * 8;
+  for (unsigned m = marked; m;) {
+    unsigned mine = m;  // the grp-th lowest marked lane of this round
+#pragma unroll
+    for (int g = 1; g < kGroups; ++g)
+      if (grp >= g) mine &= mine - 1;
+    const bool have = mine != 0u;
+    const int from = have ? __ffs(mine) - 1 : 0;
+    const int cl = __shfl_sync(0xffffffffu, cell, from);
+    const float dn = __shfl_sync(0xffffffffu, denom, from);
+    if (have) {
+      float e[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) e[k] = ld_in(img + (size_t)(kPer * sub + k) * cells + cl);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) e[k] = spvo_exp(e[k]);
+      // shared-reciprocal division when the denominator is comfortably inside the normal range (always, for finite
+      // network outputs of sane magnitude); otherwise the stand-alone IEEE division
+      if (fast_div && dn > 0x1p-60f && dn < 0x1p60f) {
+        const float rcp = __frcp_rn(dn);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) e[k] = div_by_rcp(e[k], dn, rcp);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) e[k] = __fdiv_rn(e[k], dn);
+      }
+      const int hc = cl / Wc, wc = cl - hc * Wc;
+      const int px = kPer * sub;  // first pixel (8 * row + col) of this lane
+      float* dst = heat_img + (size_t)(8 * hc + (px >> 3)) * W + 8 * wc + (px & 7);
+      if constexpr (kPer == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(e[0], e[1]);
+      } else {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(e[0], e[1], e[2], e[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(e[4], e[5], e[6], e[7]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) m &= m - 1;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kHeatThreads, 4)
-k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __restrict__ cellmax, int Hc, int Wc,
-               int fast_div) {
+k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __restrict__ cellmax,
+               const uint32_t* __restrict__ spill_thr, int b0, uint32_t conf_bits, int Hc, int Wc, int fast_div) {
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
-  if (cell >= cells) return;
-  const T* src = semi + (size_t)b * 65 * cells + cell;
-  float e[64];
+  const T* img = semi + (size_t)b * 65 * cells;
+  bool store = false;
+  float denom = 1.0f;
+  if (cell < cells) {
+    const T* src = img + cell;
+    float s = 0.0f;
+    float m1 = 0.0f, m2 = 0.0f;  // largest and second largest exponential of the cell (m2 == m1 on ties)
+    int arg = 0;                 // pixel index 8 * row + col of the largest
+    float x[64];                 // every channel of the cell in flight (8 KB per warp)
 #pragma unroll
-  for (int c = 0; c < 64; ++c) e[c] = ld_in(src + (size_t)c * cells);
-  const float xd = ld_in(src + (size_t)64 * cells);
-  float s = 0.0f;
+    for (int u = 0; u < 64; ++u) x[u] = ld_in(src + (size_t)u * cells);
 #pragma unroll
-  for (int c = 0; c < 64; ++c) {
-    e[c] = spvo_exp(e[c]);
-    s = __fadd_rn(s, e[c]);
-  }
-  s = __fadd_rn(s, spvo_exp(xd));
-  const float denom = __fadd_rn(s, 0.00001f);
-  const int hc = cell / Wc, wc = cell - hc * Wc;
-  const int W = Wc * 8;
-  float* dst = heat + (size_t)b * (size_t)(Hc * 8) * W + (size_t)(8 * hc) * W + 8 * wc;
-  float m1 = 0.0f, m2 = 0.0f;  // largest and second largest pixel of the cell (m2 == m1 on ties)
-  int arg = 0;                 // pixel index 8 * row + col of the largest
-  auto rows = [&](auto divide) {
+    for (int u = 0; u < 64; u += 2) {
+      float e[2];
+      spvo_exp_x2(x[u], x[u + 1], e[0], e[1]);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float p[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p[j] = divide(e[8 * r + j]);
-        m2 = fmaxf(m2, fminf(m1, p[j]));
-        arg = p[j] > m1 ? 8 * r + j : arg;
-        m1 = fmaxf(m1, p[j]);
+      for (int v = 0; v < 2; ++v) {
+        s = __fadd_rn(s, e[v]);
+        m2 = fmaxf(m2, fminf(m1, e[v]));
+        arg = e[v] > m1 ? u + v : arg;
+        m1 = fmaxf(m1, e[v]);
       }
-      reinterpret_cast<float4*>(dst + (size_t)r * W)[0] = make_float4(p[0], p[1], p[2], p[3]);
-      reinterpret_cast<float4*>(dst + (size_t)r * W)[1] = make_float4(p[4], p[5], p[6], p[7]);
     }
-  };
-  // shared-reciprocal division when the denominator is comfortably inside the normal range (always, for finite
-  // network outputs of sane magnitude); otherwise the stand-alone IEEE division
-  if (fast_div && denom > 0x1p-60f && denom < 0x1p60f) {
-    const float rcp = __frcp_rn(denom);
-    rows([&](float a) { return div_by_rcp(a, denom, rcp); });
-  } else {
-    rows([&](float a) { return __fdiv_rn(a, denom); });
+    s = __fadd_rn(s, spvo_exp(ld_in(src + (size_t)64 * cells)));
+    denom = __fadd_rn(s, 0.00001f);
+    // Per-cell record for k_detect: .x = bits of the cell maximum, .y = bits of the second largest pixel with the
+    // low 6 bits replaced by the argmax (meaningful when the maximum is unique -- the only case k_detect uses it).
+    // Cells that cannot hold a candidate of the current range are skipped there; cells whose second pixel is below
+    // the range yield their single candidate straight from the record.
+    const float p1 = __fdiv_rn(m1, denom), p2 = __fdiv_rn(m2, denom);
+    const uint2 rec = make_uint2(fbits(p1), (fbits(p2) & ~63u) | (uint32_t)arg);
+    cellmax[(size_t)b * cells + cell] = rec;
+    store = cell_spilled(rec.y, __ldg(spill_thr + b0 + b), conf_bits);
   }
-  // Per-cell record for k_detect: .x = bits of the cell maximum, .y = bits of the second largest pixel with the
-  // low 6 bits replaced by the argmax.  Cells that cannot hold a first-chunk candidate are skipped; cells whose
-  // second pixel is below the chunk's bound yield their single candidate without touching the heatmap.
-  cellmax[(size_t)b * cells + cell] = make_uint2(fbits(m1), (fbits(m2) & ~63u) | (uint32_t)arg);
+  // Store the 64 heat values of the cells k_detect is expected to open (two or more candidates above the bound its
+  // walk reached on this image slot last time).  The logits are re-read (this warp loaded their sectors a moment ago)
+  // so that the main loop does not have to keep 64 exponentials alive.  No shared memory, no block barrier: a warp
+  // with one or two marked cells takes them one at a time (lane l: pixels 2l, 2l+1), a warp with more takes four at
+  // a time (8 lanes per cell, one heat row each, 8 loads in flight per lane).
+  const unsigned marked = __ballot_sync(0xffffffffu, store);
+  if (marked == 0u) return;
+  float* hb = heat + (size_t)b * (size_t)(Hc * 8) * (Wc * 8);
+  if (__popc(marked) <= 2) store_heat_cells<32>(marked, img, hb, cell, denom, cells, Wc, fast_div);
+  else store_heat_cells<8>(marked, img, hb, cell, denom, cells, Wc, fast_div);
 }
 
 // Self-check used by tests (spvo_debug_div_check): counts operand pairs on which the shared-reciprocal division
@@ -136,7 +197,11 @@ cudaError_t launch_div_check(Handle* h, const uint32_t* a_bits, const uint32_t* 
 // the reference's column-major candidate list (NN:205-217).
 // ------------------------------------------------------------------------------------------------
 struct DetectParams {
-  const float* heat;
+  const float* heat;     // [B, H, W] heat values of the cells k_softmax_heat chose to store (cell_spilled)
+  uint32_t* spill_thr;   // [B] per image slot: threshold k_softmax_heat used; rewritten for the next call
+  const void* semi;      // [B, 65, cells] detector logits (fp32 or fp16): other multi-candidate cells are recomputed
+  int semi_f16;
+  int fast_div;          // shared-reciprocal division allowed (conf_thresh >= 1e-20)
   const uint2* cellmax;  // [B, cells] per-cell (max bits, second-max bits | argmax) records of the heatmap
   unsigned long long* list;  // [B, kListCap] global scratch: candidate keys of the current generation
   int H, W;
@@ -160,51 +225,89 @@ constexpr int kDetectThreads = 512;
 constexpr uint32_t kInfBits = 0x7F800000u;
 typedef unsigned long long u64;
 
-struct Scan {  // running (x, y) of a thread's current float4 while striding over the heatmap
-  int x, y, dx, dy;
-};
-
 __device__ __forceinline__ u64 make_key(uint32_t bits, int x, int y, int H) {
   return ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
 }
 
-// Visit every pixel of the image once (float4 granularity, uniform trip count per warp), kScanU
-// independent 16-byte loads in flight per thread.  fn(selected, bits, x, y) is called for the four
-// pixels of a float4 only when some lane of the warp has a selected pixel.
-constexpr int kScanU = 8;
-template <class Pred, class Fn>
-__device__ __forceinline__ void scan_heat(const float* __restrict__ heat, int H, int W, Pred pred, Fn fn) {
-  const int n4 = (H * W) >> 2;
-  const int S = kDetectThreads * 4;
-  const int dy = S / W, dx = S - dy * W;
-  int p0 = threadIdx.x * 4;
-  int y = p0 / W, x = p0 - y * W;
-  for (int base = 0; base < n4; base += kScanU * kDetectThreads) {
-    float4 v[kScanU];
+// The detector logits of one image, [65][cells], fp32 or fp16.
+struct SemiView {
+  const void* base;
+  int f16, cells, Wc;
+  int fast_div;
+};
+__device__ __forceinline__ float semi_at(const SemiView& sv, int c, int cell) {
+  const size_t o = (size_t)c * sv.cells + cell;
+  return sv.f16 ? __half2float(__ldg(reinterpret_cast<const __half*>(sv.base) + o))
+                : __ldg(reinterpret_cast<const float*>(sv.base) + o);
+}
+
+// Heat values of a set of cells, recomputed from the logits with k_softmax_heat's arithmetic (NN:266-326: exp,
+// channel sum in channel order, + 1e-5, one IEEE division per pixel).  The cells are cell_list[0 .. ncell) or, when
+// cell_list is null, the cells 0 .. ncell-1.  kStageCells cells per round: all threads first fill a [65][64] table
+// of exponentials in shared memory (a warp reads one channel of 32 listed cells: coalesced where the cells are
+// neighbours), then thread (j, r) = (tid % 64, tid / 64) sums cell j's column in order and divides the 8 values of
+// heat row r.  fn(ok, bits[8], x0, y) is called once per round by EVERY thread (it may use warp collectives):
+// bits[k] = heat(y, x0 + k) when ok.
+constexpr int kStageCells = 64;
+constexpr int kStageFloats = 65 * kStageCells;
+static_assert(kDetectThreads == 8 * kStageCells, "one thread per (cell, heat row)");
+constexpr int kStageIt = (65 + 7) / 8;  // channels r, r + 8, ... of a cell: 9 independent loads per thread
+template <typename T>
+__device__ __forceinline__ void load_logits(const T* __restrict__ base, int cells, int cell, int r, bool ok, float (&x)[kStageIt]) {
 #pragma unroll
-    for (int u = 0; u < kScanU; ++u) {
-      const int i4 = base + u * kDetectThreads + threadIdx.x;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i4 < n4) v[u] = __ldg(reinterpret_cast<const float4*>(heat) + i4);
-    }
+  for (int it = 0; it < kStageIt; ++it) {
+    const int c = r + 8 * it;
+    x[it] = (ok && c < 65) ? ld_in(base + (size_t)c * cells + cell) : 0.0f;
+  }
+}
+template <class Fn>
+__device__ __forceinline__ void visit_cells(const SemiView& sv, const uint16_t* cell_list, int ncell, float* stage, Fn fn) {
+  const int tid = threadIdx.x, j = tid & (kStageCells - 1), r = tid >> 6;
+  auto cell_of = [&](int i) { return i < ncell ? (cell_list ? (int)cell_list[i] : i) : -1; };
+  auto load = [&](int cell, float (&x)[kStageIt]) {  // the element type is tested once per round, not per load
+    if (sv.f16) load_logits(reinterpret_cast<const __half*>(sv.base), sv.cells, cell, r, cell >= 0, x);
+    else load_logits(reinterpret_cast<const float*>(sv.base), sv.cells, cell, r, cell >= 0, x);
+  };
+  float x[kStageIt];
+  int cell = cell_of(j);
+  load(cell, x);
+  for (int base = 0; base < ncell; base += kStageCells) {
+    const bool ok = cell >= 0;
 #pragma unroll
-    for (int u = 0; u < kScanU; ++u) {
-      const bool in = base + u * kDetectThreads + threadIdx.x < n4;
-      const uint32_t b0 = fbits(v[u].x), b1 = fbits(v[u].y), b2 = fbits(v[u].z), b3 = fbits(v[u].w);
-      const bool s0 = in && pred(b0), s1 = in && pred(b1), s2 = in && pred(b2), s3 = in && pred(b3);
-      if (__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) {
-        fn(s0, b0, x, y);
-        fn(s1, b1, x + 1, y);
-        fn(s2, b2, x + 2, y);
-        fn(s3, b3, x + 3, y);
-      }
-      x += dx;
-      y += dy;
-      if (x >= W) {
-        x -= W;
-        ++y;
+    for (int it = 0; it < kStageIt; ++it) {
+      const int c = r + 8 * it;
+      if (c < 65) stage[c * kStageCells + j] = spvo_exp(x[it]);
+    }
+    __syncthreads();
+    // the next round's logits travel while this round is summed, divided and filtered
+    const int cell_next = cell_of(base + kStageCells + j);
+    if (base + kStageCells < ncell) load(cell_next, x);
+    uint32_t bits[8];
+    int x0 = 0, y = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bits[k] = 0u;
+    if (ok) {
+      float s = 0.0f;
+#pragma unroll 13
+      for (int c = 0; c < 65; ++c) s = __fadd_rn(s, stage[c * kStageCells + j]);
+      const float denom = __fadd_rn(s, 0.00001f);
+      const int hc = cell / sv.Wc, wc = cell - hc * sv.Wc;
+      x0 = 8 * wc;
+      y = 8 * hc + r;
+      // shared-reciprocal division when the denominator is comfortably inside the normal range (always, for finite
+      // network outputs of sane magnitude); otherwise the stand-alone IEEE division
+      if (sv.fast_div && denom > 0x1p-60f && denom < 0x1p60f) {
+        const float rcp = __frcp_rn(denom);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bits[k] = fbits(div_by_rcp(stage[(8 * r + k) * kStageCells + j], denom, rcp));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bits[k] = fbits(__fdiv_rn(stage[(8 * r + k) * kStageCells + j], denom));
       }
     }
+    fn(ok, bits, x0, y);
+    cell = cell_next;
+    __syncthreads();  // the table is refilled by the next round
   }
 }
 
@@ -220,22 +323,19 @@ __device__ __forceinline__ int score_bin(uint32_t bits) {
 //   * a cell whose maximum is below lo holds nothing;
 //   * a cell whose maximum lies in [lo, hi) and whose second largest pixel is below lo yields its single candidate
 //     straight from the record;
-//   * every other contributing cell (second largest pixel >= lo) is fetched (8 rows x 32 B) and filtered.
+//   * every other contributing cell (second largest pixel >= lo) has its 64 heat values recomputed from the
+//     logits (visit_cells) and filtered.
 // (second | 63) bounds the second largest pixel from above.  Returns the number of keys in [lo, hi) (the first
 // `list_cap` are stored); bins[] is incremented for every one of them.
 constexpr int kListCap = 16384;
 
-__device__ void fetch_listed_cells(const float* __restrict__ heat, int H, int W, uint32_t conf_bits, u64 lo, u64 hi,
+// Stored cells: half a warp per cell reads its 8 rows x 32 B of the heatmap.
+__device__ void fetch_spilled_cells(const float* __restrict__ heat, int H, int W, uint32_t conf_bits, u64 lo, u64 hi,
                                    const uint16_t* cell_list, int ncell, u64* __restrict__ list, int list_cap,
                                    unsigned* bins, int* s_count) {
   const int Wc = W >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
-  // candidate scores: above conf, finite, and inside [lo_b, hi_b]; scores EQUAL to lo_b / hi_b need the full key
-  const uint32_t lo_cmp = max(conf_bits + 1u, lo_b), hi_cmp = min(hi_b, kInfBits - 1u);
-  const uint32_t span = hi_cmp >= lo_cmp ? hi_cmp - lo_cmp : 0u;
-  if (hi_cmp < lo_cmp) return;
-  const bool lo_edge = (uint32_t)lo != 0u, hi_edge = hi_b < kInfBits;  // the boundary cuts through a score value
   // half a warp per cell: lane l16 reads row l16/2, float4 l16&1 of the cell's 8x8 block
   const int l16 = lane & 15, half = lane >> 4, row = l16 >> 1, part = l16 & 1;
   constexpr int kCU = 4;  // cells (16-byte loads) in flight per thread
@@ -258,29 +358,21 @@ __device__ void fetch_listed_cells(const float* __restrict__ heat, int H, int W,
         v[u] = __ldg(reinterpret_cast<const float4*>(heat + (size_t)cy[u] * W + cx[u]));
       }
     }
-    // Hits are rare (a few pixels per fetched cell).  Pass 1 marks pixels whose SCORE lies in the range with one
-    // subtract + one unsigned compare per pixel; pass 2 (lanes with marks only) builds the keys and settles pixels whose
-    // score equals a boundary score by the full key; then the warp reserves its key slots with ONE scan + ONE atomic.
+    // Hits are rare (a few pixels per fetched cell), so each thread first marks its hits in a 32-bit mask, the warp
+    // reserves its key slots with ONE scan + ONE shared atomic, and only then are the keys built and stored.
     uint32_t mask = 0u;
 #pragma unroll
     for (int u = 0; u < kCU; ++u) {
       const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (fbits(pv[e]) - lo_cmp <= span) mask |= 1u << (4 * u + e);  // padding loads are 0.0f: below lo_cmp
-    }
-    if (mask && (lo_edge | hi_edge)) {  // some score bits coincide with a range boundary: compare full keys
-#pragma unroll
-      for (int u = 0; u < kCU; ++u) {
-        const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t bts = fbits(pv[e]);
-          if ((mask >> (4 * u + e) & 1u) && (bts == lo_b || bts == hi_b)) {
-            const u64 key = make_key(bts, cx[u] + e, cy[u], H);
-            if (!(key >= lo && key < hi)) mask &= ~(1u << (4 * u + e));
-          }
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t bts = fbits(pv[e]);
+        bool s = ok[u] && bts > conf_bits && bts >= lo_b && bts <= hi_b && bts < kInfBits;
+        if (s && (bts == lo_b || bts == hi_b)) {  // boundary score: full key comparison
+          const u64 key = make_key(bts, cx[u] + e, cy[u], H);
+          s = key >= lo && key < hi;
         }
+        mask |= (s ? 1u : 0u) << (4 * u + e);
       }
     }
     const int cnt = __popc(mask);
@@ -302,8 +394,7 @@ __device__ void fetch_listed_cells(const float* __restrict__ heat, int H, int W,
         for (int e = 0; e < 4; ++e) {
           if (mask & (1u << (4 * u + e))) {
             const uint32_t bts = fbits(pv[e]);
-            const u64 key = make_key(bts, cx[u] + e, cy[u], H);
-            if (slot < list_cap) list[slot] = key;
+            if (slot < list_cap) list[slot] = make_key(bts, cx[u] + e, cy[u], H);
             atomicAdd(&bins[score_bin(bts)], 1u);
             ++slot;
           }
@@ -313,14 +404,61 @@ __device__ void fetch_listed_cells(const float* __restrict__ heat, int H, int W,
   }
 }
 
-__device__ int collect_to_list(const float* __restrict__ heat, const uint2* __restrict__ cellmax, int H, int W,
+// Cells that were not stored: recomputed from the logits.
+__device__ void fetch_listed_cells(const SemiView& sv, int H, uint32_t conf_bits, u64 lo, u64 hi,
+                                   const uint16_t* cell_list, int ncell, u64* __restrict__ list, int list_cap,
+                                   unsigned* bins, int* s_count, float* stage) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lo_b = (uint32_t)(lo >> 32), hi_b = (uint32_t)(hi >> 32);
+  visit_cells(sv, cell_list, ncell, stage, [&](bool ok, const uint32_t (&bits)[8], int x0, int y) {
+    // Hits are rare (a few pixels per cell), so each thread first marks its hits in a mask, the warp reserves its
+    // key slots with ONE scan + ONE shared atomic, and only then are the keys built and stored.
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t bts = bits[k];
+      bool s = ok && bts > conf_bits && bts >= lo_b && bts <= hi_b && bts < kInfBits;
+      if (s && (bts == lo_b || bts == hi_b)) {  // boundary score: full key comparison
+        const u64 key = make_key(bts, x0 + k, y, H);
+        s = key >= lo && key < hi;
+      }
+      mask |= (s ? 1u : 0u) << k;
+    }
+    const int cnt = __popc(mask);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int basei = 0;
+    if (lane == 31 && inc > 0) basei = atomicAdd(s_count, inc);
+    basei = __shfl_sync(0xffffffffu, basei, 31);
+    int slot = basei + inc - cnt;
+    if (mask) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (mask & (1u << k)) {
+          if (slot < list_cap) list[slot] = make_key(bits[k], x0 + k, y, H);
+          atomicAdd(&bins[score_bin(bits[k])], 1u);
+          ++slot;
+        }
+      }
+    }
+  });
+}
+
+__device__ int collect_to_list(const SemiView& sv, const float* __restrict__ heat, uint32_t thr_bits,
+                               const uint2* __restrict__ cellmax, int H, int W,
                                uint32_t conf_bits, u64 lo, u64 hi, u64* __restrict__ list, int list_cap,
-                               unsigned* bins, uint16_t* cell_list, int cl_cap, int* s_count, int* s_ncell) {
+                               unsigned* bins, uint16_t* cell_list, int cl_cap, int* s_count, int* s_ncell,
+                               int* s_ncell2, float* stage) {
   const int Wc = W >> 3, cells = (H >> 3) * Wc;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     *s_count = 0;
     *s_ncell = 0;
+    *s_ncell2 = 0;
   }
   __syncthreads();
   const uint32_t lo_b = (uint32_t)(lo >> 32);
@@ -346,13 +484,23 @@ __device__ int collect_to_list(const float* __restrict__ heat, const uint2* __re
         key = make_key(mb, 8 * wc + (a & 7), 8 * hc + (a >> 3), H);
         single = key >= lo && key < hi;
       }
-      const unsigned mm = __ballot_sync(0xffffffffu, multi);
+      // stored cells are listed from the front of cell_list, the others from its back (never colliding: flushed below)
+      const bool stored = multi && cell_spilled(rec[u].y, thr_bits, conf_bits);
+      const unsigned mm = __ballot_sync(0xffffffffu, stored);
       if (mm) {
         int basei = 0;
         const int leader = __ffs(mm) - 1;
         if (lane == leader) basei = atomicAdd(s_ncell, __popc(mm));
         basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (multi) cell_list[basei + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)c;  // never past cl_cap: flushed below
+        if (stored) cell_list[basei + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)c;
+      }
+      const unsigned mu = __ballot_sync(0xffffffffu, multi && !stored);
+      if (mu) {
+        int basei = 0;
+        const int leader = __ffs(mu) - 1;
+        if (lane == leader) basei = atomicAdd(s_ncell2, __popc(mu));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (multi && !stored) cell_list[cl_cap - 1 - (basei + __popc(mu & ((1u << lane) - 1u)))] = (uint16_t)c;
       }
       const unsigned ms = __ballot_sync(0xffffffffu, single);
       if (ms) {
@@ -369,11 +517,15 @@ __device__ int collect_to_list(const float* __restrict__ heat, const uint2* __re
     }
     __syncthreads();
     // fetch the listed cells before the list can overflow (a block of records adds at most kPU * threads cells)
-    if (*s_ncell + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
-      const int ncell = *s_ncell;
-      fetch_listed_cells(heat, H, W, conf_bits, lo, hi, cell_list, ncell, list, list_cap, bins, s_count);
+    if (*s_ncell + *s_ncell2 + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
+      const int ncell = *s_ncell, ncell2 = *s_ncell2;
+      fetch_spilled_cells(heat, H, W, conf_bits, lo, hi, cell_list, ncell, list, list_cap, bins, s_count);
+      fetch_listed_cells(sv, H, conf_bits, lo, hi, cell_list + cl_cap - ncell2, ncell2, list, list_cap, bins, s_count, stage);
       __syncthreads();
-      if (threadIdx.x == 0) *s_ncell = 0;
+      if (threadIdx.x == 0) {
+        *s_ncell = 0;
+        *s_ncell2 = 0;
+      }
       __syncthreads();
     }
   }
@@ -459,9 +611,10 @@ __device__ u64 radix_select_list(const u64* __restrict__ list, int n_list, u64 h
 }
 
 // Exact radix select: returns the m-th largest key among candidate keys < hi (unique keys), or
-// `floor_key` when fewer than m remain.  8 passes of 8 bits over the heatmap (slow path only).
-__device__ u64 radix_select(const float* heat, int H, int W, uint32_t conf_bits, u64 hi, int m, u64 floor_key,
-                            unsigned* s_hist, u64* s_prefix, int* s_want) {
+// `floor_key` when fewer than m remain.  8 passes of 8 bits, each recomputing every cell of the image (slow path
+// only: one score bin alone overflows the candidate list, i.e. > 12 k exactly tied pixels).
+__device__ u64 radix_select(const SemiView& sv, int H, uint32_t conf_bits, u64 hi, int m, u64 floor_key,
+                            unsigned* s_hist, u64* s_prefix, int* s_want, float* stage) {
   if (threadIdx.x == 0) {
     *s_prefix = 0;
     *s_want = m;
@@ -472,18 +625,17 @@ __device__ u64 radix_select(const float* heat, int H, int W, uint32_t conf_bits,
     for (int i = threadIdx.x; i < 256; i += kDetectThreads) s_hist[i] = 0;
     __syncthreads();
     const u64 prefix = *s_prefix;
-    scan_heat(
-        heat, H, W, [&](uint32_t b) { return b > conf_bits && b <= hi_b && b < kInfBits; },
-        [&](bool s, uint32_t b, int x, int y) {
-          u64 key = make_key(b, x, y, H);
-          s = s && key < hi && (pass == 0 || (key >> (shift + 8)) == prefix);
-          unsigned act = __ballot_sync(0xffffffffu, s);
-          if (s) {
-            unsigned digit = (unsigned)(key >> shift) & 255u;
-            unsigned peers = __match_any_sync(act, digit);
-            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
-          }
-        });
+    visit_cells(sv, nullptr, sv.cells, stage, [&](bool ok, const uint32_t (&bits)[8], int x0, int y) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t b = bits[k];
+        if (ok && b > conf_bits && b <= hi_b && b < kInfBits) {
+          const u64 key = make_key(b, x0 + k, y, H);
+          if (key < hi && (pass == 0 || (key >> (shift + 8)) == prefix))
+            atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+      }
+    });
     __syncthreads();
     if (threadIdx.x == 0) {
       int want = *s_want, cum = 0, d = 255;
@@ -747,12 +899,19 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
   unsigned* bins = reinterpret_cast<unsigned*>(state + 2 * cap); // [kHistBins] score-bin histogram (chunk sizing)
   u64* list = p.list + (size_t)b * kListCap;                     // this image's candidate list (global, L2-resident)
-  __shared__ int s_count, s_want, s_emitted;
+  __shared__ int s_count, s_want, s_emitted, s_ncell2;
   __shared__ int s_res[3];
   __shared__ u64 s_prefix;
   __shared__ unsigned s_warp_tot[kDetectThreads / 32];
 
   const float* heat = p.heat + (size_t)b * H * W;
+  const uint32_t thr_bits = p.spill_thr[b];  // the threshold k_softmax_heat stored cells by on this call
+  SemiView sv;
+  sv.base = static_cast<const unsigned char*>(p.semi) + (size_t)b * 65 * cells * (p.semi_f16 ? 2 : 4);
+  sv.f16 = p.semi_f16; sv.cells = cells; sv.Wc = Wc; sv.fast_div = p.fast_div;
+  // table of exponentials for visit_cells: inside the key buffer (idle while candidates are gathered), behind the
+  // 256 radix-select counters that alias its start
+  float* stage = reinterpret_cast<float*>(keys) + 256;
   const uint2* cellmax = p.cellmax + (size_t)b * cells;
   const uint32_t conf_bits = fbits(fmaxf(p.conf, 0.0f));
   const u64 floor_key = ((u64)conf_bits + 1ull) << 32;  // smallest possible candidate key (score > conf)
@@ -771,6 +930,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   // heuristic; overflow is detected exactly and repaired, so the result always equals full sort + sequential walk.
   bool slow = false;
   u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
+  u64 lowest = ~0ull;  // lowest generation bound the walk needed (the next call's storing threshold derives from it)
   int walked = 0;
   while (true) {
     // ---- G1: range of the generation from the histogram of cell MAXIMA (an estimate) ----------------
@@ -794,8 +954,8 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     while (true) {
       for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
       __syncthreads();
-      n_list = collect_to_list(heat, cellmax, H, W, conf_bits, lo_pre, hi_pre, list, kListCap, bins, next, cap, &s_count,
-                               &s_want);
+      n_list = collect_to_list(sv, heat, thr_bits, cellmax, H, W, conf_bits, lo_pre, hi_pre, list, kListCap, bins, next,
+                               cap, &s_count, &s_want, &s_ncell2, stage);
       __syncthreads();
       if (n_list <= kListCap) break;
       slow = true;  // more candidates than the list holds: raise the lower bound exactly and gather again
@@ -804,7 +964,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
                                      : (s_res[2] > 0 ? bin_to_lo_key(s_res[0] - 1, floor_key) : 0ull);
       __syncthreads();
       if (lo2 <= lo_pre) {  // one score bin alone overflows the list (massive ties): exact select on the heatmap
-        lo2 = radix_select(heat, H, W, conf_bits, hi_pre, kListCap * 3 / 4, floor_key, s_hist, &s_prefix, &s_want);
+        lo2 = radix_select(sv, H, conf_bits, hi_pre, kListCap * 3 / 4, floor_key, s_hist, &s_prefix, &s_want, stage);
         __syncthreads();
       }
       lo_pre = lo2;
@@ -1037,6 +1197,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512), max(512LL, need + need / 4 + 128));
       __syncthreads();
     }
+    lowest = lo_pre;
     if (done) break;
     hi_pre = lo_pre;
   }
@@ -1080,6 +1241,8 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   if (tid == 0) {
     p.n_out[b] = n_emit;
     if (slow) atomicAdd(&p.counters[0], 1ull);
+    // next call on this image slot: store the cells whose second value reaches 0.9 x the lowest bound needed now
+    p.spill_thr[b] = fbits(__fmul_rn(0.9f, __uint_as_float((uint32_t)(lowest >> 32))));
   }
 }
 
@@ -1334,6 +1497,12 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
 // ------------------------------------------------------------------------------------------------
 // host-side launcher
 // ------------------------------------------------------------------------------------------------
+static uint32_t fbits_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, sizeof u);
+  return u;
+}
+
 static size_t detect_smem_bytes(int H, int W, int K, int cap) {
   const int ww = (W + 31) >> 5;
   const size_t cells = (size_t)(H / 8) * (W / 8);
@@ -1365,16 +1534,18 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
   const int fast_div = cfg.conf_thresh >= 1e-20f ? 1 : 0;
   {
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
+    const uint32_t conf_bits = fbits_host(fmaxf(cfg.conf_thresh, 0.0f));
     if (in_f16)
-      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, cellmax, Hc, Wc,
-                                                          fast_div);
+      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, cellmax,
+                                                          h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
     else
-      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, cellmax, Hc, Wc,
-                                                         fast_div);
+      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, cellmax,
+                                                         h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
   }
   if (K > 0) {
     DetectParams p;
-    p.heat = heat; p.cellmax = cellmax; p.list = h->cand_list + (size_t)b0 * kListCap; p.H = H; p.W = W;
+    p.semi = semi; p.semi_f16 = in_f16; p.fast_div = fast_div; p.cellmax = cellmax;
+    p.heat = heat; p.spill_thr = h->spill_thr + b0; p.list = h->cand_list + (size_t)b0 * kListCap; p.H = H; p.W = W;
     p.conf = cfg.conf_thresh;
     p.dist = cfg.dist_thresh; p.border = cfg.border_remove; p.K = K;
     p.kpts = kpts; p.scores = scores; p.n_out = n_out; p.counters = h->counters;
