@@ -1,7 +1,7 @@
 #!/bin/bash
-# usage: scripts/ncu_hot.sh <report.ncu-rep> <kernel regex> [top N]  -- hottest CUDA source lines by warp-stall samples
-rep=$1; k=$2; n=${3:-25}
-ncu -i "$rep" --page source --csv --print-source cuda,sass --kernel-name "regex:$k" 2>/dev/null > /tmp/_src.csv
+# usage: scripts/ncu_hot.sh <report.ncu-rep> <kernel regex> [top N] [launch index]  -- hottest CUDA source lines by warp-stall samples
+rep=$1; k=$2; n=${3:-25}; skip=${4:-}
+ncu -i "$rep" --page source --csv --print-source cuda,sass --kernel-name "regex:$k" ${skip:+--launch-skip $skip --launch-count 1} 2>/dev/null > /tmp/_src.csv
 python - "$n" <<'PY'
 import csv, sys
 n=int(sys.argv[1])

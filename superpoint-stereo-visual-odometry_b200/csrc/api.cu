@@ -336,11 +336,19 @@ static int check_match_cfg(Handle* h, const spvo_match_cfg* cfg, int dim) {
   return SPVO_OK;
 }
 
-static int pick_algorithm(const spvo_match_cfg* cfg, int max_rows, int max_cols) {
-  // AUTO: the tensor-core path unless the problems are too small to fill a 128 x 128 tile.
+static int pick_algorithm(const spvo_match_cfg* cfg, int max_rows, int max_cols, int P) {
+  // AUTO, from scripts/match_sweep.py on B200 (profiles/match_sweep_r02.json).  The tensor path costs six launches
+  // (~35 us for one small problem, flat up to N ~ 1000) and then ~1 ps per pair; the exact fp32 path two to three
+  // launches (~19 us) and 45 ps (NN, ratio) to 77 ps (cross-check) per pair while a single problem cannot fill the
+  // GPU, ~15 ps per pair in a large batch.  Cross-overs: one problem of N = M = 384 (cross-check), ~576 (NN), ~640
+  // (ratio test); 444 problems (148 stereo pairs) of 64 keypoints.
   int alg = cfg->algorithm;
-  if (alg == SPVO_MATCHER_AUTO)
-    alg = ((long long)max_rows * max_cols >= 128 * 128) ? SPVO_MATCHER_TENSOR : SPVO_MATCHER_EXACT_FP32;
+  if (alg == SPVO_MATCHER_AUTO) {
+    const long long pairs = (long long)max_rows * max_cols;
+    const long long side = cfg->mode == SPVO_MATCH_NN_CROSSCHECK ? 384 : cfg->mode == SPVO_MATCH_KNN_RATIO ? 640 : 576;
+    alg = (pairs <= side * side && pairs * (long long)(P > 0 ? P : 1) <= 1500000LL) ? SPVO_MATCHER_EXACT_FP32
+                                                                                   : SPVO_MATCHER_TENSOR;
+  }
   if (max_rows > 8192 || max_cols > 8192) alg = SPVO_MATCHER_EXACT_FP32;  // packed shortlist keys carry 13 index bits
   return alg;
 }
@@ -348,7 +356,7 @@ static int pick_algorithm(const spvo_match_cfg* cfg, int max_rows, int max_cols)
 static int run_match(Handle* h, const MatchProblem* probs, int P, int max_rows, int max_cols,
                      const spvo_match_cfg* cfg, spvo_dmatch* out, int* n_matches, int* q2t, int out_stride,
                      bool operands_ready = false) {
-  const int alg = pick_algorithm(cfg, max_rows, max_cols);
+  const int alg = pick_algorithm(cfg, max_rows, max_cols, P);
   if (alg == SPVO_MATCHER_TENSOR)
     CK(launch_match_tc(h, probs, P, max_rows, max_cols, *cfg, out, n_matches, q2t, out_stride, operands_ready));
   else
@@ -539,7 +547,7 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
   if (rc) return rc;
   // tensor matcher: decode writes each image's bf16 operand straight into slot = image index;
   // slot max_batch holds the carried last-left image of the previous batch
-  const bool tensor = pick_algorithm(&cfg->match, K, K) == SPVO_MATCHER_TENSOR;
+  const bool tensor = pick_algorithm(&cfg->match, K, K, 2 * F) == SPVO_MATCHER_TENSOR;
   const int carry_slot = h->max_batch;
   TcSink sink;
   if (tensor) CK(tc_prepare_slots(h, h->max_batch + 1, h->max_k, 2 * h->max_batch, &sink));

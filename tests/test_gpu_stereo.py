@@ -82,7 +82,8 @@ def test_stereo_batch_host_and_device(spvo, oracle, mode):
     ds, dd = torch.from_numpy(semi).cuda(), torch.from_numpy(desc).cuda()
     for b in range(NB):
         dout = fe.alloc_stereo_out(F, K, device="cuda")
-        fe.stereo_batch_device(ds[b * F:(b + 1) * F], dd[b * F:(b + 1) * F], F, H, W, dout, **kw)
+        # AUTO picks by problem size (api.cu pick_algorithm); the device form pins the tensor-core matcher
+        fe.stereo_batch_device(ds[b * F:(b + 1) * F], dd[b * F:(b + 1) * F], F, H, W, dout, algorithm=S.MATCHER_TENSOR, **kw)
         torch.cuda.synchronize()
         _check_batch(S, {k: v.cpu().numpy() for k, v in dout.items()}, ref, b * F, F, K)
     fe.close()
