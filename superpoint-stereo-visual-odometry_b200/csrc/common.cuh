@@ -3,6 +3,8 @@
 // order unless an explicit __fmaf_rn is written, so results match oracle/spvo_oracle.cpp bit for bit.
 #pragma once
 
+#include <utility>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -244,6 +246,17 @@ struct LaunchScope {
 
 __device__ __forceinline__ uint32_t fbits(float f) { return __float_as_uint(f); }
 
+// Programmatic dependent launch.  Every kernel of the stereo step starts with chain_enter(): it waits until the
+// preceding kernel in the stream has completed and its writes are visible (griddepcontrol.wait; a no-op for a plain
+// launch), then lets the NEXT kernel's blocks be scheduled (griddepcontrol.launch_dependents) -- they sit at their
+// own chain_enter() until this grid is done.  Nothing is read or written before the wait, so the only thing that
+// overlaps is launch latency and block scheduling.  Measured: -6 us per call for one small stereo pair with plain
+// launches; nothing at 148 pairs per call (the gaps there are ramp-up and tails, not launch latency).
+__device__ __forceinline__ void chain_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // exp as specified by the oracle (oracle/spvo_oracle.cpp: oracle_exp): Cephes/Eigen-style expf
 // written as explicit IEEE fp32 operations.  Replaces Eigen's packet exp at NN:271.
 __device__ __forceinline__ float spvo_exp(float x0) {
@@ -314,6 +327,46 @@ __device__ __forceinline__ void spvo_exp_x2(float xa0, float xb0, float& ea, flo
   f32x2_unpack(f32x2_mul(y, f32x2_pack(sa, sb)), pa, pb);
   ea = fmaxf(pa, xa0);
   eb = fmaxf(pb, xb0);
+}
+
+
+// Launch with the programmatic-stream-serialization attribute (see chain_enter).  ONLY for kernels that begin with
+// chain_enter().  SPVO_PDL=0 in the environment turns the attribute off (A/B measurements).
+inline bool chained_launch_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPVO_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  // not while the stream is being captured: measured on B200 (640x192, K = 500, one pair per call) plain launches gain
+  // 6 us per call from the attribute, but a graph whose edges are programmatic replays 4 us SLOWER than plain edges
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (chained_launch_enabled() && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  lc.attrs = at;
+  lc.numAttrs = n;
+  return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 
 }  // namespace spvo

@@ -120,6 +120,7 @@ template <typename T>
 __global__ void __launch_bounds__(kHeatThreads, 4)
 k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __restrict__ cellmax,
                const uint32_t* __restrict__ spill_thr, int b0, uint32_t conf_bits, int Hc, int Wc, int fast_div) {
+  chain_enter();
   const int b = blockIdx.y;
   const int cells = Hc * Wc;
   const int cell = blockIdx.x * kHeatThreads + threadIdx.x;
@@ -883,6 +884,7 @@ constexpr uint16_t kNil = 0xFFFFu;
 
 __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  chain_enter();
   const int b = blockIdx.x;
   const int H = p.H, W = p.W, K = p.K, cap = p.cap, d = p.dist, bd = p.border;
   const int ww = (W + 31) >> 5;  // bitmap words per row
@@ -1336,6 +1338,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_desc_planes(const T* __restrict__ desc, const int4* __restrict__ kp_par, const int* __restrict__ n_out,
               float* __restrict__ tmp, int cells, int K, int plane_pitch, int Kp) {
+  chain_enter();
   extern __shared__ __align__(16) unsigned char sp_raw[];  // kCP planes, each plane_pitch elements of T
   T* sp = reinterpret_cast<T*>(sp_raw);
   const int b = blockIdx.y, cg = blockIdx.x;
@@ -1419,6 +1422,7 @@ k_desc_planes(const T* __restrict__ desc, const int4* __restrict__ kp_par, const
 __global__ void __launch_bounds__(256)
 k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K, int Kp,
                  TcSink sink) {
+  chain_enter();
   __shared__ float s[32][257];
   const int b = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1536,11 +1540,12 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
     const uint32_t conf_bits = fbits_host(fmaxf(cfg.conf_thresh, 0.0f));
     if (in_f16)
-      k_softmax_heat<__half><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const __half*>(semi), heat, cellmax,
-                                                          h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
+      e = launch_chained(k_softmax_heat<__half>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const __half*>(semi),
+                         heat, cellmax, h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
     else
-      k_softmax_heat<float><<<g1, kHeatThreads, 0, st>>>(reinterpret_cast<const float*>(semi), heat, cellmax,
-                                                         h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
+      e = launch_chained(k_softmax_heat<float>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const float*>(semi),
+                         heat, cellmax, h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
+    if (e != cudaSuccess) return e;
   }
   if (K > 0) {
     DetectParams p;
@@ -1570,7 +1575,7 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
       return e;
     {
       LaunchScope ls(h, KID_DETECT);
-      k_detect<<<B, kDetectThreads, smem, st>>>(p);
+      if ((e = launch_chained(k_detect, dim3(B), dim3(kDetectThreads), smem, st, 1, p)) != cudaSuccess) return e;
     }
     if (streaming) {
       if ((e = cudaFuncSetAttribute(k_desc_planes<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
@@ -1595,13 +1600,14 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
         {
           LaunchScope ls(h, KID_DESC_PLANES);
           if (in_f16)
-            k_desc_planes<__half><<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(
-                reinterpret_cast<const __half*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K, n_out + g0,
-                tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
+            e = launch_chained(k_desc_planes<__half>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
+                               reinterpret_cast<const __half*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K,
+                               n_out + g0, tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
           else
-            k_desc_planes<float><<<dim3(256 / kCP, gb), 256, smem_planes, st>>>(
-                reinterpret_cast<const float*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K, n_out + g0,
-                tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
+            e = launch_chained(k_desc_planes<float>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
+                               reinterpret_cast<const float*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K,
+                               n_out + g0, tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
+          if (e != cudaSuccess) return e;
         }
         TcSink sg = sk;
         if (sg.xb) {
@@ -1610,8 +1616,10 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
           sg.opmax += g0;
         }
         LaunchScope ls(h, KID_DESC_NORM);
-        k_desc_normalize<<<dim3((rows + 31) / 32, gb), 256, 0, st>>>(tmp + (size_t)g0 * 256 * Kp, n_out + g0,
-                                                                    desc_out + (size_t)g0 * K * 256, K, Kp, sg);
+        if ((e = launch_chained(k_desc_normalize, dim3((rows + 31) / 32, gb), dim3(256), 0, st, 1,
+                                tmp + (size_t)g0 * 256 * Kp, n_out + g0, desc_out + (size_t)g0 * K * 256, K, Kp, sg)) !=
+            cudaSuccess)
+          return e;
       }
     } else if (desc && desc_out) {
       dim3 g3((K + 7) / 8, B);

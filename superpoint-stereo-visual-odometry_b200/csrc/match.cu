@@ -177,6 +177,7 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
                    const float* __restrict__ row_d, const int* __restrict__ col_best, int max_rows, int max_cols,
                    int mode, float ratio, spvo_dmatch* __restrict__ out, int* __restrict__ n_matches,
                    int* __restrict__ q2t, int out_stride, const FilterArgs flt) {
+  chain_enter();
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const MatchProblem pr = probs[blockIdx.x];
@@ -232,6 +233,7 @@ k_finalize_matches(const MatchProblem* __restrict__ probs, const int* __restrict
 
 __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, const int* n_rows,
                                  int slot_stride_rows, const int* q_slot, const int* t_slot, int P) {
+  chain_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const int qs = q_slot[p], ts = t_slot[p];
@@ -253,6 +255,7 @@ __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, co
 __global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_out, const int* n_out,
                                         const float* carry_desc, const int* carry_n, int F, int K, int carry_slot,
                                         const spvo_keypoint* kpts, float band) {
+  chain_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= 2 * F) return;
   MatchProblem pr;
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(1024)
 k_consistency(int F, int K, const spvo_dmatch* __restrict__ matches, const int* __restrict__ n_matches,
               const int* __restrict__ q2t, const uint8_t* __restrict__ keep, const int* __restrict__ carry_map,
               spvo_quad* __restrict__ quads, int* __restrict__ n_quads, const CopyList cl) {
+  chain_enter();
   if ((int)blockIdx.x >= F) {
     // copy blocks: the carry for the next batch (last left image's descriptors / keypoints / count / matcher operand,
     // L<->R map) -- kCopyBlocks blocks per segment, 16-byte accesses where the segment allows
@@ -420,9 +424,11 @@ cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, in
                                  int out_stride) {
   {
     LaunchScope ls(h, KID_FINALIZE);
-    k_finalize_matches<<<P, 1024, 0, h->stream>>>(probs, h->row_best, h->row_d, h->col_best, mr, mc, cfg.mode,
-                                                  cfg.ratio, out, n_matches, q2t, out_stride, h->fin_filter);
+    const cudaError_t e = launch_chained(k_finalize_matches, dim3(P), dim3(1024), 0, h->stream, 1, probs, h->row_best,
+                                         h->row_d, h->col_best, mr, mc, (int)cfg.mode, cfg.ratio, out, n_matches, q2t,
+                                         out_stride, h->fin_filter);
     h->fin_filter = FilterArgs();  // one-shot
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
@@ -461,8 +467,9 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
   if (P == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
-    k_setup_problems<<<(P + 127) / 128, 128, 0, h->stream>>>(probs, desc_base, n_rows, slot_stride_rows, q_slot,
-                                                            t_slot, P);
+    const cudaError_t e = launch_chained(k_setup_problems, dim3((P + 127) / 128), dim3(128), 0, h->stream, 1, probs,
+                                         desc_base, n_rows, slot_stride_rows, q_slot, t_slot, P);
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
@@ -472,8 +479,9 @@ cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const f
   if (F == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
-    k_setup_stereo_problems<<<(2 * F + 127) / 128, 128, 0, h->stream>>>(probs, desc_out, n_out, h->carry_desc,
-                                                                       h->carry_n, F, K, carry_slot, kpts, band);
+    const cudaError_t e = launch_chained(k_setup_stereo_problems, dim3((2 * F + 127) / 128), dim3(128), 0, h->stream, 1,
+                                         probs, desc_out, n_out, h->carry_desc, h->carry_n, F, K, carry_slot, kpts, band);
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
@@ -484,8 +492,9 @@ cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* match
   const int fb = quads ? F : 0;  // frames whose quadruples are wanted
   if (fb + cl.n == 0) return cudaSuccess;
   LaunchScope ls(h, KID_CONSISTENCY);
-  k_consistency<<<fb + cl.n * kCopyBlocks, 1024, 0, h->stream>>>(fb, K, matches, n_matches, q2t, keep, carry_map, quads,
-                                                                 n_quads, cl);
+  const cudaError_t e = launch_chained(k_consistency, dim3(fb + cl.n * kCopyBlocks), dim3(1024), 0, h->stream, 1, fb, K,
+                                       matches, n_matches, q2t, keep, carry_map, quads, n_quads, cl);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -393,7 +393,12 @@ template <bool kUnit, bool kCols, bool kMask>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restrict__ probs,
           const float* __restrict__ nrm, const unsigned* __restrict__ opmax, RowRec* __restrict__ row_rec,
-          ColRec* __restrict__ col_rec, int cap, uint32_t idesc, int n_items, uint32_t r256) {
+          ColRec* __restrict__ col_rec, int cap, uint32_t idesc, int n_items, uint32_t r256,
+          int* __restrict__ zero_counters, int n_zero) {
+  chain_enter();
+  // the rerank / fallback worklist counters of this call (used from k_tc_triage on): cleared here instead of by a
+  // memset node, which would break the chain of programmatic launches
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_counters[i] = 0;
   extern __shared__ uint8_t smem_raw[];
   const int nrb = cap / kBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -728,6 +733,7 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
             int cap, int max_rows, int max_cols, int* __restrict__ row_best, float* __restrict__ row_d,
             int* __restrict__ col_best, int* __restrict__ rr_count, int* __restrict__ rr_list,
             Short* __restrict__ shortl, float eps_rel, int unit) {
+  chain_enter();
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -857,6 +863,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
             int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
             int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
             float eps_rel, int unit, const int* __restrict__ rr_count, const int* __restrict__ rr_list) {
+  chain_enter();
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
@@ -968,6 +975,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
 __global__ void __launch_bounds__(256)
 k_tc_fill_dist(const MatchProblem* __restrict__ probs, int mode, int max_rows, int max_cols,
                const int* __restrict__ row_best, float* __restrict__ row_d, const int* __restrict__ col_best) {
+  chain_enter();
   const int p = blockIdx.y;
   const MatchProblem pr = probs[p];
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
@@ -1006,6 +1014,7 @@ k_tc_fallback(const MatchProblem* __restrict__ probs, int P, int mode, const flo
               int max_rows, int max_cols, const int* __restrict__ fb_count, const int* __restrict__ fb_list,
               int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
               unsigned long long* __restrict__ counters) {
+  chain_enter();
   // The scan of a queued row group is latency-bound per CTA (a warp keeps two train rows in flight), so the columns
   // are split over a cluster of kFbSplit CTAs; their per-warp shortlists meet in the shared memory of cluster rank 0
   // (distributed shared memory), which finishes the rows.
@@ -1379,9 +1388,8 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       LaunchScope ls(h, KID_TC_PREP);
       k_tc_prep<<<dim3((cap + 31) / 32, 2 * P), 256, 0, st>>>(probs, w->xb, w->nrm, w->opmax, cap, 0);
     }
-    // one memset for both worklist counters: fb_count sits right behind the ndir rerank counters of this call
+    // both worklist counters are cleared by k_tc_gemm: fb_count sits right behind the ndir rerank counters of this call
     int* const fb_count = w->rr_count + ndir;
-    if ((e = cudaMemsetAsync(w->rr_count, 0, (size_t)2 * ndir * sizeof(int), st)) != cudaSuccess) return e;
     const float eps_rel = w->fp16 ? kEpsRelFp16 : kEpsRelBf16;
     // unit-norm operands (written by decode, fp16) use constant key scaling; arbitrary CV_32F inputs scale by the
     // operands' largest norms (tc_scale)
@@ -1397,45 +1405,39 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       LaunchScope ls(h, KID_TC_GEMM);
       const int n_items = (cap / kBM) * P;  // ONE Gram matrix per problem: both directions come from its epilogue
       const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
-      kern<<<grid, kTcThreads, smem, st>>>(w->tmap, probs, w->nrm, w->opmax, w->row_rec, w->col_rec, cap,
-                                           make_idesc(w->fp16), n_items, 256u);
+      if ((e = launch_chained(kern, dim3(grid), dim3(kTcThreads), smem, st, 1, w->tmap, probs, w->nrm, w->opmax, w->row_rec,
+                              w->col_rec, cap, make_idesc(w->fp16), n_items, 256u, w->rr_count, 2 * ndir)) != cudaSuccess)
+        return e;
     }
     {
       LaunchScope ls(h, KID_TC_TRIAGE);
-      k_tc_triage<<<dim3((cap + 255) / 256, ndir), 256, 0, st>>>(probs, P, cfg.mode, w->nrm, w->opmax, w->row_rec,
-                                                               w->col_rec, cap, mr, mc, h->row_best, h->row_d,
-                                                               h->col_best, w->rr_count, w->rr_list, w->shortl, eps_rel,
-                                                               unit);
+      if ((e = launch_chained(k_tc_triage, dim3((cap + 255) / 256, ndir), dim3(256), 0, st, 1, probs, P, (int)cfg.mode,
+                              w->nrm, w->opmax, w->row_rec, w->col_rec, cap, mr, mc, h->row_best, h->row_d, h->col_best,
+                              w->rr_count, w->rr_list, w->shortl, eps_rel, unit)) != cudaSuccess)
+        return e;
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
-      k_tc_rerank<<<dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir), 256, 0, st>>>(
-          probs, P, cfg.mode, cfg.ratio, w->nrm, w->opmax, w->shortl, cap, mr, mc, h->row_best, h->row_d, h->col_best,
-          fb_count, w->fb_list, h->counters, eps_rel, unit, w->rr_count, w->rr_list);
+      if ((e = launch_chained(k_tc_rerank, dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir),
+                              dim3(256), 0, st, 1, probs, P, (int)cfg.mode, cfg.ratio, w->nrm, w->opmax, w->shortl, cap, mr,
+                              mc, h->row_best, h->row_d, h->col_best, fb_count, w->fb_list, h->counters, eps_rel, unit,
+                              w->rr_count, w->rr_list)) != cudaSuccess)
+        return e;
     }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
-      cudaLaunchConfig_t lc = {};
-      lc.gridDim = dim3(ndir * kFbSplit);
-      lc.blockDim = dim3(256);
-      lc.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = kFbSplit;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      lc.attrs = at;
-      lc.numAttrs = 1;
       const int* fbc = fb_count;
       const int* fbl = w->fb_list;
-      if ((e = cudaLaunchKernelEx(&lc, k_tc_fallback, probs, P, (int)cfg.mode, (const float*)w->nrm, cap, mr, mc, fbc, fbl,
-                                  h->row_best, h->row_d, h->col_best, h->counters)) != cudaSuccess)
+      if ((e = launch_chained(k_tc_fallback, dim3(ndir * kFbSplit), dim3(256), 0, st, kFbSplit, probs, P, (int)cfg.mode,
+                              (const float*)w->nrm, cap, mr, mc, fbc, fbl, h->row_best, h->row_d, h->col_best,
+                              h->counters)) != cudaSuccess)
         return e;
     }
     if (cfg.mode != SPVO_MATCH_KNN_RATIO) {
       LaunchScope ls(h, KID_TC_FILL);
-      k_tc_fill_dist<<<dim3((max_rows + 15) / 16, P), 256, 0, st>>>(probs, cfg.mode, mr, mc, h->row_best, h->row_d,
-                                                                   h->col_best);
+      if ((e = launch_chained(k_tc_fill_dist, dim3((max_rows + 15) / 16, P), dim3(256), 0, st, 1, probs, (int)cfg.mode, mr,
+                              mc, h->row_best, h->row_d, h->col_best)) != cudaSuccess)
+        return e;
     }
   }
   return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
