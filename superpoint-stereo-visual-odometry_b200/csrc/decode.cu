@@ -882,6 +882,13 @@ __device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
 enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
 
+#ifdef SPVO_PHASE_TIMING
+__device__ long long g_phase_clk[64 * 16];
+__device__ int g_phase_rounds[64];
+#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chain_enter();
@@ -934,15 +941,24 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
   u64 lowest = ~0ull;  // lowest generation bound the walk needed (the next call's storing threshold derives from it)
   int walked = 0;
+  PHASE(0);
   while (true) {
     // ---- G1: range of the generation from the histogram of cell MAXIMA (an estimate) ----------------
     for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
     __syncthreads();
     {
       const uint32_t hi_b = (uint32_t)(hi_pre >> 32);
-      for (int c = tid; c < cells; c += kDetectThreads) {
-        const uint32_t mb = __ldg(&cellmax[c].x);
-        if (mb > conf_bits && mb < kInfBits && mb <= hi_b) atomicAdd(&bins[score_bin(mb)], 1u);
+      constexpr int kGU = 8;  // records in flight per thread (the loop is a chain of L2 round trips otherwise)
+      for (int c0 = 0; c0 < cells; c0 += kGU * kDetectThreads) {
+        uint32_t mb[kGU];
+#pragma unroll
+        for (int u = 0; u < kGU; ++u) {
+          const int c = c0 + u * kDetectThreads + tid;
+          mb[u] = c < cells ? __ldg(&cellmax[c].x) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kGU; ++u)
+          if (mb[u] > conf_bits && mb[u] < kInfBits && mb[u] <= hi_b) atomicAdd(&bins[score_bin(mb[u])], 1u);
       }
     }
     __syncthreads();
@@ -951,6 +967,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     const int gen_cells = max(s_res[1], 1);  // cells whose maximum lies in the generation's range
     if (lo_pre >= hi_pre) lo_pre = floor_key;
     __syncthreads();
+    PHASE(1);
     // ---- G2: gather [lo_pre, hi_pre) into the list; exact bins --------------------------------------
     int n_list;
     while (true) {
@@ -971,6 +988,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       }
       lo_pre = lo2;
     }
+    PHASE(2);
     // ---- G3: chunks of the walk ---------------------------------------------------------------------
     u64 hi = hi_pre;
     // Clustered heatmaps (a real network: ~7 candidates per contributing cell, most of them suppressed by their
@@ -1020,6 +1038,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
         __syncthreads();
         bitonic_sort_desc(keys, n_pad);
       }
+      PHASE(3);
       whole = false;
       walked += n;
     for (int i = tid; i <= cells; i += kDetectThreads) head[i] = 0;
@@ -1072,6 +1091,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       __syncthreads();
     }
 
+    PHASE(4);
     // ---- B: fixed-point rounds ---------------------------------------------------------------------
     if (d == 0) {
       for (int i = tid; i < n; i += kDetectThreads)
@@ -1127,6 +1147,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       }
     }
 
+    PHASE(5);
     // ---- C: emit kept in-border candidates in rank order, up to K ------------------------------------
     {
       const int seg = (n + kDetectThreads - 1) / kDetectThreads;
@@ -1204,6 +1225,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     hi_pre = lo_pre;
   }
 
+  PHASE(6);
   // ---- outputs ---------------------------------------------------------------------------------
   const int n_emit = min(s_emitted, K);
   spvo_keypoint* kp = p.kpts + (size_t)b * K;
@@ -1240,6 +1262,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       p.kp_par[(size_t)b * K + i] = par;
     }
   }
+  PHASE(7);
   if (tid == 0) {
     p.n_out[b] = n_emit;
     if (slow) atomicAdd(&p.counters[0], 1ull);
@@ -1677,3 +1700,9 @@ size_t decode_smem_required(int H, int W, int K) { return detect_smem_bytes(H, W
 size_t decode_list_bytes_per_image() { return (size_t)kListCap * sizeof(u64); }
 
 }  // namespace spvo
+
+#ifdef SPVO_PHASE_TIMING
+extern "C" int spvo_debug_phase_clocks(long long* out) {  // [64][16] clock64 stamps of k_detect's phases; diagnostic builds only
+  return cudaMemcpyFromSymbol(out, spvo::g_phase_clk, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
