@@ -518,8 +518,10 @@ __device__ int collect_to_list(const SemiView& sv, const float* __restrict__ hea
     }
     __syncthreads();
     // fetch the listed cells before the list can overflow (a block of records adds at most kPU * threads cells)
-    if (*s_ncell + *s_ncell2 + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
-      const int ncell = *s_ncell, ncell2 = *s_ncell2;
+    // every thread must see the SAME counts: the next round's atomics may not start before all have read them
+    const int ncell = *s_ncell, ncell2 = *s_ncell2;
+    __syncthreads();
+    if (ncell + ncell2 + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
       fetch_spilled_cells(heat, H, W, conf_bits, lo, hi, cell_list, ncell, list, list_cap, bins, s_count);
       fetch_listed_cells(sv, H, conf_bits, lo, hi, cell_list + cl_cap - ncell2, ncell2, list, list_cap, bins, s_count, stage);
       __syncthreads();

@@ -901,7 +901,9 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       while (nc < kTop && jx[nc] >= 0 && g[nc] <= g[0] + slack) ++nc;
       if (!(sl.bound > g[0] + slack)) full = true;
     } else if (jx[1] < 0) {
-      nc = 1;  // a single train column: the second best does not exist (the ratio test then fails in finalize)
+      // a single admissible train column: the second best does not exist (the ratio test then fails in finalize);
+      // none at all (every column masked out): nothing to evaluate, the row has no match
+      nc = jx[0] < 0 ? 0 : 1;
     } else {
       nc = 2;
       while (nc < kTop && jx[nc] >= 0 && g[nc] <= g[1] + slack) ++nc;
