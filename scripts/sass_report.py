@@ -1,6 +1,7 @@
 """Opcode histogram of the hot kernels from the built objects (cuobjdump -sass): the Blackwell-native evidence
 (UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load, LDTM = tcgen05.ld, UBLKCP = bulk copy, UTCBAR = tcgen05.commit,
-SYNCS = mbarrier, LDGSTS = cp.async, VIMNMX / VIMNMX3 = the shortlist networks) kept under profiles/ so that it
+SYNCS = mbarrier, LDGSTS = cp.async, VIMNMX / VIMNMX3 = the shortlist networks, FFMA2 / FMUL2 / FADD2 = packed
+fp32, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents) kept under profiles/ so that it
 survives a rebuild.   usage: python scripts/sass_report.py > profiles/sass_r02.txt"""
 import collections
 import os
@@ -33,6 +34,6 @@ for obj, kernels in WANT.items():
         for op, n in c.items():
             base[op.split(".")[0]] += n
         print("   " + ", ".join(f"{op} {n}" for op, n in base.most_common(18)))
-        special = {op: n for op, n in c.items() if re.match(r"(UTCHMMA|UTMALDG|LDTM|STTM|UBLKCP|UTCBAR|UTCATOMSWS|SYNCS|LDGSTS|VIMNMX3|UCGABAR|MEMBAR|ATOMS|RED|REDUX)", op)}
+        special = {op: n for op, n in c.items() if re.match(r"(UTCHMMA|UTMALDG|LDTM|STTM|UBLKCP|UTCBAR|UTCATOMSWS|SYNCS|LDGSTS|VIMNMX3|UCGABAR|MEMBAR|ATOMS|RED|REDUX|FFMA2|FMUL2|FADD2|ACQBULK|PREEXIT)", op)}
         if special:
             print("   evidence: " + ", ".join(f"{op} x{n}" for op, n in sorted(special.items())))
