@@ -13,8 +13,11 @@ through ONE C-ABI call (spvo_stereo_batch_device / spvo_stereo_batch).
             batches larger than L2), timed with CUDA events on the launching stream, max over ranks
   e2e       the same metric through the host-buffer C-ABI call (spvo_stereo_batch): pinned host
             inputs -> H2D -> kernels -> D2H of keypoints / matches / maps, every step
-  roofline  dominant kernel of the step, timed live with CUDA events inside the timed region
-            (spvo_profile_*), against MEASURED_PEAKS.json
+  roofline  dominant kernel of the step, timed live with CUDA events (spvo_profile_*: two event records
+            around every launch on the launching stream) over a second pass of the same K steps right
+            after the timed region, against MEASURED_PEAKS.json; the primary value is timed without
+            those events (they serialise launches the library otherwise overlaps) and the profiled
+            pass's own step time is reported next to it (kernel_timing)
   cpu_baseline  the CPU oracle (port of the reference decode + cv::BFMatcher arithmetic) timed on this
             host's cores on a bounded sample (rank 0, N = 1 only)
 
@@ -275,8 +278,7 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     barrier()
-    fe.profile_enable(True)
-    fe.profile_read()
+    # THE timed region: exactly K steps, nothing but the library's own launches on the stream
     l0 = fe.kernel_launches
     clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -287,8 +289,21 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
-    prof = fe.profile_read()
     launches = fe.kernel_launches - l0
+    # the same K steps once more with the library's per-kernel CUDA events (spvo_profile_*: two event records around
+    # every launch on the launching stream).  The events serialise what the plain region may overlap (programmatic
+    # dependent launch, the matcher's concurrent tail), so this pass is a little slower; it is reported next to the
+    # primary number and is what the per-kernel table and the rooflines are computed from.
+    fe.profile_enable(True)
+    fe.profile_read()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + args.steps + i)
+    p1.record(stream)
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
+    prof = fe.profile_read()
     fe.profile_enable(False)
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -564,6 +579,10 @@ def run_ours(args, rank, world, local_rank):
             "strong": strong,
             "latency": latency,
             "kernels": kernels,
+            "kernel_timing": {"ms_per_step_with_kernel_events": ms_profiled / args.steps,
+                              "note": "kernels / roofline / decode_roofline / tensor_roofline come from a second pass "
+                                      "over the same K steps with two CUDA-event records around every launch on the "
+                                      "launching stream; the primary value is timed without them"},
             "cpu_baseline": cpu_baseline,
         }))
     fe.close()

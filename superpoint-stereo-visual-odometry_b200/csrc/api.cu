@@ -195,6 +195,7 @@ static int decode_device_impl(Handle* h, const void* semi, const void* desc, int
   int rc = check_decode_args(h, semi, B, H, W, cfg, kpts_out, n_out);
   if (rc) return rc;
   DeviceGuard g(h->device);
+  h->chain_launches = B <= 8;
   CK(launch_decode(h, semi, desc, in_f16, B, H, W, *cfg, kpts_out, desc_out, n_out, scores_out));
   return SPVO_OK;
 }
@@ -225,6 +226,7 @@ static int decode_host_impl(Handle* h, const void* semi, const void* desc, int i
   const bool with_desc = desc && desc_out;
   CK(cudaMemcpyAsync(h->st_semi, semi, (size_t)B * 65 * cells * esz, cudaMemcpyHostToDevice, st));
   if (with_desc) CK(cudaMemcpyAsync(h->st_desc, desc, (size_t)B * 256 * cells * esz, cudaMemcpyHostToDevice, st));
+  h->chain_launches = B <= 8;
   CK(launch_decode(h, h->st_semi, with_desc ? h->st_desc : nullptr, in_f16, B, H, W, *cfg, h->st_kpts,
                    with_desc ? h->st_desc_out : nullptr, h->st_n, scores_out ? h->st_scores : nullptr));
   CK(cudaMemcpyAsync(n_out, h->st_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -376,6 +378,7 @@ static int match_device_impl(Handle* h, const float* q, int N, const float* t, i
   spvo_match_cfg c = *cfg;
   c.flags = (q_kpts && t_kpts && band >= 0.0f) ? (c.flags | SPVO_MATCH_FLAG_ROW_BAND) : (c.flags & ~SPVO_MATCH_FLAG_ROW_BAND);
   CK(launch_set_problem(h, h->probs, q, N, t, M, q_kpts, t_kpts, band));
+  h->chain_launches = true;
   return run_match(h, h->probs, 1, N, M, &c, out, n_matches, q2t, N > 0 ? N : 1);
 }
 
@@ -435,6 +438,7 @@ static int match_host_impl(Handle* h, const float* q, int N, const float* t, int
   spvo_match_cfg c = *cfg;
   c.flags = masked ? (c.flags | SPVO_MATCH_FLAG_ROW_BAND) : (c.flags & ~SPVO_MATCH_FLAG_ROW_BAND);
   CK(launch_set_problem(h, h->probs, h->st_q, N, h->st_t, M, d_qk, d_tk, band));
+  h->chain_launches = true;
   rc = run_match(h, h->probs, 1, N, M, &c, h->st_matches, h->st_nm, h->st_q2t, N);
   if (rc) return rc;
   CK(cudaMemcpyAsync(n_matches, h->st_nm, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -481,6 +485,7 @@ int spvo_match_batch_device(spvo_handle hh, const float* desc_base, const int* n
     h->probs_cap = P;
   }
   CK(launch_setup_problems(h, h->probs, desc_base, n_rows, slot_stride_rows, q_slot, t_slot, P));
+  h->chain_launches = P <= 8;
   return run_match(h, h->probs, P, max_rows, max_rows, cfg, out, n_matches, q2t, max_rows > 0 ? max_rows : 1);
 }
 
@@ -547,6 +552,7 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
   if (rc) return rc;
   // tensor matcher: decode writes each image's bf16 operand straight into slot = image index;
   // slot max_batch holds the carried last-left image of the previous batch
+  h->chain_launches = F <= 4;  // latency-shaped calls: overlap launch latency along the kernel chain (common.cuh)
   const bool tensor = pick_algorithm(&cfg->match, K, K, 2 * F) == SPVO_MATCHER_TENSOR;
   const int carry_slot = h->max_batch;
   TcSink sink;

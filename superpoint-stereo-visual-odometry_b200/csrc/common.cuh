@@ -190,6 +190,7 @@ struct Handle {
   cudaEvent_t aux_done[2] = {nullptr, nullptr};
   cudaEvent_t aux_fork = nullptr;
   int decode_subbatches = 0;  // 0 = automatic
+  bool chain_launches = false;  // programmatic dependent launch for this call's kernels (small calls only)
   // host-form stereo batches: H2D of the next chunk overlaps compute of the current one
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -330,8 +331,11 @@ __device__ __forceinline__ void spvo_exp_x2(float xa0, float xb0, float& ea, flo
 }
 
 
-// Launch with the programmatic-stream-serialization attribute (see chain_enter).  ONLY for kernels that begin with
-// chain_enter().  SPVO_PDL=0 in the environment turns the attribute off (A/B measurements).
+// Launch, optionally with the programmatic-stream-serialization attribute (see chain_enter; ONLY for kernels that
+// begin with chain_enter()).  `chained` = Handle::chain_launches, which the entry points set for SMALL calls only:
+// measured on B200, the attribute saves 10 us of a 100 us single-pair call but makes a 148-pair step 7.8 % SLOWER
+// (1.213 vs 1.126 ms: the early-resident blocks of the next kernel get in the way of the current one's tail).
+// SPVO_PDL=0 in the environment turns the attribute off everywhere (A/B measurements).
 inline bool chained_launch_enabled() {
   static const bool on = [] {
     const char* e = getenv("SPVO_PDL");
@@ -340,8 +344,8 @@ inline bool chained_launch_enabled() {
   return on;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                  int cluster_x, Args&&... args) {
+inline cudaError_t launch_chained(bool chained, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t st, int cluster_x, Args&&... args) {
   cudaLaunchConfig_t lc = {};
   lc.gridDim = grid;
   lc.blockDim = block;
@@ -352,7 +356,8 @@ inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block,
   // not while the stream is being captured: measured on B200 (640x192, K = 500, one pair per call) plain launches gain
   // 6 us per call from the attribute, but a graph whose edges are programmatic replays 4 us SLOWER than plain edges
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (chained_launch_enabled() && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+  if (chained && chained_launch_enabled() && cudaStreamIsCapturing(st, &cs) == cudaSuccess &&
+      cs == cudaStreamCaptureStatusNone) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -367,6 +372,18 @@ inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block,
   lc.attrs = at;
   lc.numAttrs = n;
   return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
+// Two auxiliary streams + fork / join events per handle (decode sub-batches, the matcher's concurrent tail), created
+// on first use.
+inline cudaError_t ensure_aux_streams(Handle* h) {
+  if (h->aux_stream[0]) return cudaSuccess;
+  cudaError_t e;
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  return cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming);
 }
 
 }  // namespace spvo

@@ -1565,10 +1565,10 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
     LaunchScope ls(h, KID_SOFTMAX_HEAT);
     const uint32_t conf_bits = fbits_host(fmaxf(cfg.conf_thresh, 0.0f));
     if (in_f16)
-      e = launch_chained(k_softmax_heat<__half>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const __half*>(semi),
+      e = launch_chained(h->chain_launches, k_softmax_heat<__half>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const __half*>(semi),
                          heat, cellmax, h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
     else
-      e = launch_chained(k_softmax_heat<float>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const float*>(semi),
+      e = launch_chained(h->chain_launches, k_softmax_heat<float>, g1, dim3(kHeatThreads), 0, st, 1, reinterpret_cast<const float*>(semi),
                          heat, cellmax, h->spill_thr, b0, conf_bits, Hc, Wc, fast_div);
     if (e != cudaSuccess) return e;
   }
@@ -1600,7 +1600,7 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
       return e;
     {
       LaunchScope ls(h, KID_DETECT);
-      if ((e = launch_chained(k_detect, dim3(B), dim3(kDetectThreads), smem, st, 1, p)) != cudaSuccess) return e;
+      if ((e = launch_chained(h->chain_launches, k_detect, dim3(B), dim3(kDetectThreads), smem, st, 1, p)) != cudaSuccess) return e;
     }
     if (streaming) {
       if ((e = cudaFuncSetAttribute(k_desc_planes<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_planes)) != cudaSuccess)
@@ -1625,11 +1625,11 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
         {
           LaunchScope ls(h, KID_DESC_PLANES);
           if (in_f16)
-            e = launch_chained(k_desc_planes<__half>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
+            e = launch_chained(h->chain_launches, k_desc_planes<__half>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
                                reinterpret_cast<const __half*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K,
                                n_out + g0, tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
           else
-            e = launch_chained(k_desc_planes<float>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
+            e = launch_chained(h->chain_launches, k_desc_planes<float>, dim3(256 / kCP, gb), dim3(256), smem_planes, st, 1,
                                reinterpret_cast<const float*>(desc) + (size_t)g0 * 256 * cells, kp_par + (size_t)g0 * K,
                                n_out + g0, tmp + (size_t)g0 * 256 * Kp, cells, K, plane_pitch, Kp);
           if (e != cudaSuccess) return e;
@@ -1641,7 +1641,7 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
           sg.opmax += g0;
         }
         LaunchScope ls(h, KID_DESC_NORM);
-        if ((e = launch_chained(k_desc_normalize, dim3((rows + 31) / 32, gb), dim3(256), 0, st, 1,
+        if ((e = launch_chained(h->chain_launches, k_desc_normalize, dim3((rows + 31) / 32, gb), dim3(256), 0, st, 1,
                                 tmp + (size_t)g0 * 256 * Kp, n_out + g0, desc_out + (size_t)g0 * K * 256, K, Kp, sg)) !=
             cudaSuccess)
           return e;
@@ -1673,13 +1673,7 @@ cudaError_t launch_decode(Handle* h, const void* semi, const void* desc, int in_
   if (nsb > B) nsb = B;
   if (nsb <= 1) return launch_decode_range(h, semi, desc, in_f16, 0, B, H, W, cfg, kpts, desc_out, n_out, scores, sink, sink_filled);
   cudaError_t e;
-  if (!h->aux_stream[0]) {
-    for (int i = 0; i < 2; ++i) {
-      if ((e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
-      if ((e = cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-    }
-    if ((e = cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-  }
+  if ((e = ensure_aux_streams(h)) != cudaSuccess) return e;
   cudaStream_t main_st = h->stream;
   if ((e = cudaEventRecord(h->aux_fork, main_st)) != cudaSuccess) return e;
   for (int i = 0; i < 2; ++i)

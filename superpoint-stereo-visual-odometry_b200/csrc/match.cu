@@ -424,7 +424,7 @@ cudaError_t launch_finalize_only(Handle* h, const MatchProblem* probs, int P, in
                                  int out_stride) {
   {
     LaunchScope ls(h, KID_FINALIZE);
-    const cudaError_t e = launch_chained(k_finalize_matches, dim3(P), dim3(1024), 0, h->stream, 1, probs, h->row_best,
+    const cudaError_t e = launch_chained(h->chain_launches, k_finalize_matches, dim3(P), dim3(1024), 0, h->stream, 1, probs, h->row_best,
                                          h->row_d, h->col_best, mr, mc, (int)cfg.mode, cfg.ratio, out, n_matches, q2t,
                                          out_stride, h->fin_filter);
     h->fin_filter = FilterArgs();  // one-shot
@@ -467,7 +467,7 @@ cudaError_t launch_setup_problems(Handle* h, MatchProblem* probs, const float* d
   if (P == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
-    const cudaError_t e = launch_chained(k_setup_problems, dim3((P + 127) / 128), dim3(128), 0, h->stream, 1, probs,
+    const cudaError_t e = launch_chained(h->chain_launches, k_setup_problems, dim3((P + 127) / 128), dim3(128), 0, h->stream, 1, probs,
                                          desc_base, n_rows, slot_stride_rows, q_slot, t_slot, P);
     if (e != cudaSuccess) return e;
   }
@@ -479,7 +479,7 @@ cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const f
   if (F == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
-    const cudaError_t e = launch_chained(k_setup_stereo_problems, dim3((2 * F + 127) / 128), dim3(128), 0, h->stream, 1,
+    const cudaError_t e = launch_chained(h->chain_launches, k_setup_stereo_problems, dim3((2 * F + 127) / 128), dim3(128), 0, h->stream, 1,
                                          probs, desc_out, n_out, h->carry_desc, h->carry_n, F, K, carry_slot, kpts, band);
     if (e != cudaSuccess) return e;
   }
@@ -492,7 +492,7 @@ cudaError_t launch_consistency(Handle* h, int F, int K, const spvo_dmatch* match
   const int fb = quads ? F : 0;  // frames whose quadruples are wanted
   if (fb + cl.n == 0) return cudaSuccess;
   LaunchScope ls(h, KID_CONSISTENCY);
-  const cudaError_t e = launch_chained(k_consistency, dim3(fb + cl.n * kCopyBlocks), dim3(1024), 0, h->stream, 1, fb, K,
+  const cudaError_t e = launch_chained(h->chain_launches, k_consistency, dim3(fb + cl.n * kCopyBlocks), dim3(1024), 0, h->stream, 1, fb, K,
                                        matches, n_matches, q2t, keep, carry_map, quads, n_quads, cl);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();

@@ -857,6 +857,8 @@ __device__ __forceinline__ void top2_push(float d, int j, float& b0, int& x0, fl
   }
 }
 
+constexpr int kPending = -2;  // row_best / col_best of a row queued for k_tc_fallback (see k_tc_rerank, k_tc_fill_dist)
+
 __global__ void __launch_bounds__(256)
 k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
             const unsigned* __restrict__ opmax, const Short* __restrict__ shortl, int cap, int max_rows,
@@ -930,10 +932,19 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       }
     }
     if (full) {
-      // shortlist not provably complete: queue the row for k_tc_fallback (which writes its result)
+      // shortlist not provably complete: queue the row for k_tc_fallback (which writes its result).  Until then the
+      // row is marked PENDING (-2): k_tc_fill_dist may run concurrently with the fallback and must neither fill a
+      // pending row's distance nor trust a pending column's cross-check
       if (lane == 0) {
         fb_list[(size_t)dp * cap + atomicAdd(&fb_count[dp], 1)] = i;
         atomicAdd(&counters[1], 1ull);
+        if (!rev) {
+          const size_t o = ((size_t)p * max_rows + i) * 2;
+          row_best[o] = kPending;
+          row_d[o] = 0.0f;
+        } else {
+          col_best[(size_t)p * max_cols + i] = kPending;
+        }
       }
       continue;
     } else if (nc == 1 && !knn) {
@@ -988,8 +999,12 @@ k_tc_fill_dist(const MatchProblem* __restrict__ probs, int mode, int max_rows, i
   const size_t o = ((size_t)p * max_rows + (i < pr.N ? i : 0)) * 2;
   if (i < pr.N && pr.M > 0) {
     j = row_best[o];
-    need = j >= 0 && row_d[o] < 0.0f;
-    if (need && mode == SPVO_MATCH_NN_CROSSCHECK) need = col_best[(size_t)p * max_cols + j] == i;
+    need = j >= 0 && row_d[o] < 0.0f;  // a row still pending in the fallback (kPending) is filled by the fallback itself
+    if (need && mode == SPVO_MATCH_NN_CROSSCHECK) {
+      // a column pending in the (possibly concurrent) fallback may still turn out to be this row's mutual match
+      const int cb = *reinterpret_cast<const volatile int*>(col_best + (size_t)p * max_cols + j);
+      need = cb == i || cb == kPending;
+    }
   }
   if (!__any_sync(0xffffffffu, need)) return;
   const int ii = need ? i : 0, jj = need ? j : 0;
@@ -1407,40 +1422,58 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
       LaunchScope ls(h, KID_TC_GEMM);
       const int n_items = (cap / kBM) * P;  // ONE Gram matrix per problem: both directions come from its epilogue
       const int grid = n_items < h->sm_count ? n_items : h->sm_count;  // persistent: one CTA per SM
-      if ((e = launch_chained(kern, dim3(grid), dim3(kTcThreads), smem, st, 1, w->tmap, probs, w->nrm, w->opmax, w->row_rec,
+      if ((e = launch_chained(h->chain_launches, kern, dim3(grid), dim3(kTcThreads), smem, st, 1, w->tmap, probs, w->nrm, w->opmax, w->row_rec,
                               w->col_rec, cap, make_idesc(w->fp16), n_items, 256u, w->rr_count, 2 * ndir)) != cudaSuccess)
         return e;
     }
     {
       LaunchScope ls(h, KID_TC_TRIAGE);
-      if ((e = launch_chained(k_tc_triage, dim3((cap + 255) / 256, ndir), dim3(256), 0, st, 1, probs, P, (int)cfg.mode,
+      if ((e = launch_chained(h->chain_launches, k_tc_triage, dim3((cap + 255) / 256, ndir), dim3(256), 0, st, 1, probs, P, (int)cfg.mode,
                               w->nrm, w->opmax, w->row_rec, w->col_rec, cap, mr, mc, h->row_best, h->row_d, h->col_best,
                               w->rr_count, w->rr_list, w->shortl, eps_rel, unit)) != cudaSuccess)
         return e;
     }
     {
       LaunchScope ls(h, KID_TC_RERANK);
-      if ((e = launch_chained(k_tc_rerank, dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir),
+      if ((e = launch_chained(h->chain_launches, k_tc_rerank, dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir),
                               dim3(256), 0, st, 1, probs, P, (int)cfg.mode, cfg.ratio, w->nrm, w->opmax, w->shortl, cap, mr,
                               mc, h->row_best, h->row_d, h->col_best, fb_count, w->fb_list, h->counters, eps_rel, unit,
                               w->rr_count, w->rr_list)) != cudaSuccess)
         return e;
     }
+    // k_tc_fallback is a few hundred long-lived, latency-bound blocks; k_tc_fill_dist streams descriptor rows on
+    // every SM.  For the non-kNN modes they run CONCURRENTLY (fork to an auxiliary stream, join before finalize):
+    // pending rows / columns are marked by k_tc_rerank, so neither needs the other's result.  Profiling runs keep
+    // them in series on the main stream (per-kernel events).
+    static const bool overlap_env = [] {
+      const char* e = getenv("SPVO_TAIL_OVERLAP");
+      return !(e && e[0] == '0');
+    }();
+    const bool overlap = overlap_env && !h->profiling && cfg.mode != SPVO_MATCH_KNN_RATIO;
+    cudaStream_t fb_st = st;
+    if (overlap) {
+      if ((e = ensure_aux_streams(h)) != cudaSuccess) return e;
+      fb_st = h->aux_stream[0];
+      if ((e = cudaEventRecord(h->aux_fork, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(fb_st, h->aux_fork, 0)) != cudaSuccess) return e;
+    }
     {
       LaunchScope ls(h, KID_TC_FALLBACK);
       const int* fbc = fb_count;
       const int* fbl = w->fb_list;
-      if ((e = launch_chained(k_tc_fallback, dim3(ndir * kFbSplit), dim3(256), 0, st, kFbSplit, probs, P, (int)cfg.mode,
+      if ((e = launch_chained(h->chain_launches, k_tc_fallback, dim3(ndir * kFbSplit), dim3(256), 0, fb_st, kFbSplit, probs, P, (int)cfg.mode,
                               (const float*)w->nrm, cap, mr, mc, fbc, fbl, h->row_best, h->row_d, h->col_best,
                               h->counters)) != cudaSuccess)
         return e;
     }
+    if (overlap && (e = cudaEventRecord(h->aux_done[0], fb_st)) != cudaSuccess) return e;
     if (cfg.mode != SPVO_MATCH_KNN_RATIO) {
       LaunchScope ls(h, KID_TC_FILL);
-      if ((e = launch_chained(k_tc_fill_dist, dim3((max_rows + 15) / 16, P), dim3(256), 0, st, 1, probs, (int)cfg.mode, mr,
+      if ((e = launch_chained(h->chain_launches, k_tc_fill_dist, dim3((max_rows + 15) / 16, P), dim3(256), 0, st, 1, probs, (int)cfg.mode, mr,
                               mc, h->row_best, h->row_d, h->col_best)) != cudaSuccess)
         return e;
     }
+    if (overlap && (e = cudaStreamWaitEvent(st, h->aux_done[0], 0)) != cudaSuccess) return e;
   }
   return launch_finalize_only(h, probs, P, mr, mc, cfg, out, n_matches, q2t, out_stride);
 }
