@@ -274,8 +274,13 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
+    # The library replays each call signature as a CUDA graph it owns (spvo_set_graph_mode: first sight eager, second
+    # sight captured, then replayed).  The ring of R input batches x 2 carry parities gives 2R signatures, so 4R extra
+    # untimed steps precede the W warm-up steps; measured 1.117 -> 1.090 ms per 148-pair step against plain launches.
+    fe.set_graph_mode(True)
     fe.stereo_reset()
-    for i in range(args.warmup):
+    graph_steps = 4 * R
+    for i in range(graph_steps + args.warmup):
         step(i)
     barrier()
     # THE timed region: exactly K steps, nothing but the library's own launches on the stream
@@ -284,12 +289,13 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
-        step(args.warmup + i)
+        step(graph_steps + args.warmup + i)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     launches = fe.kernel_launches - l0
+    fe.set_graph_mode(False)
     # the same K steps once more with the library's per-kernel CUDA events (spvo_profile_*: two event records around
     # every launch on the launching stream).  The events serialise what the plain region may overlap (programmatic
     # dependent launch, the matcher's concurrent tail), so this pass is a little slower; it is reported next to the
@@ -299,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record(stream)
     for i in range(args.steps):
-        step(args.warmup + args.steps + i)
+        step(graph_steps + args.warmup + args.steps + i)
     p1.record(stream)
     barrier()
     ms_profiled = p0.elapsed_time(p1)
@@ -379,13 +385,15 @@ def run_ours(args, rank, world, local_rank):
         fe3.stereo_batch_device(semi3[b * F3:(b + 1) * F3], desc3[b * F3:(b + 1) * F3], F3, H, W, out3, **cfg3)
 
     steps3 = max(10, args.steps // 4)
+    fe3.set_graph_mode(True)  # as the primary region: 2 * nb3 capture steps, then the warm-up
     fe3.stereo_reset()
-    for i in range(3):
+    w3 = 2 * nb3 + 3
+    for i in range(w3):
         step3(i)
     barrier()
     e0.record(stream)
     for i in range(steps3):
-        step3(3 + i)
+        step3(w3 + i)
     e1.record(stream)
     barrier()
     t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -394,7 +402,7 @@ def run_ours(args, rank, world, local_rank):
     config3 = {"workload": "kitti_synth_1240x376_K2048_knn_ratio0.8_stereo+temporal", "value": world * steps3 * F3 / (float(t3.item()) * 1e-3),
                "unit": "pairs/s", "pairs_per_step": F3, "steps": steps3, "ms_per_step": float(t3.item()) / steps3,
                "mean_keypoints": out3["n_kpts"].float().mean().item(), "mean_matches": out3["n_matches"].float().mean().item(),
-               "scaling": "weak", "timing": "device-resident, CUDA events, max over ranks"}
+               "scaling": "weak", "timing": "device-resident, CUDA events, max over ranks; library-owned CUDA graphs"}
     fe3.close()
     del out3
 
@@ -565,6 +573,7 @@ def run_ours(args, rank, world, local_rank):
                        "match": "nn_crosscheck", "matcher_algorithm": args.algorithm,
                        "l2": f"inputs cycle through a ring of {R} batches x {in_bytes / 1e6:.0f} MB (> 126 MB L2)",
                        "frame_sharding": f"{world} contiguous ranges of {shard} frames",
+                       "launch": f"library-owned CUDA graphs (spvo_set_graph_mode), {graph_steps} untimed capture steps before the warm-up",
                        "mean_keypoints": n_kp, "mean_matches": n_m},
             "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "h2d_gbs": h2d_gbs, "h2d_ceiling_gbs": h2d_ceiling_gbs,

@@ -643,7 +643,7 @@ static int stereo_batch_device_impl(Handle* h, const void* semi, const void* des
   bool seen = false;
   for (const auto& sg : h->graph_seen) seen = seen || sg == sig;
   if (!seen) {  // first time: run eagerly, so that every workspace this signature needs exists before a capture
-    if (h->graph_seen.size() >= 16) h->graph_seen.erase(h->graph_seen.begin());
+    if (h->graph_seen.size() >= 32) h->graph_seen.erase(h->graph_seen.begin());
     h->graph_seen.push_back(sig);
     return run();
   }
@@ -666,7 +666,7 @@ static int stereo_batch_device_impl(Handle* h, const void* semi, const void* des
   const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) return cuda_fail(h, ie, "cudaGraphInstantiate");
-  if (h->graphs.size() >= 8) {
+  if (h->graphs.size() >= 16) {  // e.g. a ring of 6 input batches x 2 carry parities
     cudaGraphExecDestroy(h->graphs.front().exec);
     h->graphs.erase(h->graphs.begin());
   }
