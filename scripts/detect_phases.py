@@ -35,7 +35,9 @@ lib = ctypes.CDLL(diag)
 buf = (ctypes.c_longlong * (64 * 16))()
 assert lib.spvo_debug_phase_clocks(buf) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
-names = ["G1 cell-max histogram", "G2 gather", "G3 sort chunk", "A hash", "B jacobi", "C emit", "outputs"]
+names = ["between", "G1 cell-max histogram", "G2 gather", "chunk select+sort", "A hash", "B NMS rounds", "C emit", "D bitmap",
+         "tail", "outputs"]
 for b in range(min(2 * F, 4)):
-    d = np.diff(a[b, :8])
-    print(f"image {b}: total {a[b,7]-a[b,0]} clk  " + "  ".join(f"{n}: {int(x)}" for n, x in zip(names, d)))
+    tot = int(a[b, :12].sum())
+    print(f"image {b}: total {tot} clk, {int(a[b, 12])} chunks, {int(a[b, 13])} NMS rounds:  " +
+          "  ".join(f"{n}: {int(x)}" for n, x in zip(names, a[b, :10])) + f"  [NMS first rounds: {int(a[b, 10])}, later rounds: {int(a[b, 11])}]")

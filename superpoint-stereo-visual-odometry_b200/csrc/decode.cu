@@ -885,11 +885,18 @@ enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
 
 #ifdef SPVO_PHASE_TIMING
+// Diagnostic build only (scripts/build_diag.sh): cycles spent in each phase of k_detect, accumulated over the chunks and
+// generations of one launch, for the first 64 images.  PHASE(i) closes the interval since the previous PHASE and adds
+// it to slot i.
 __device__ long long g_phase_clk[64 * 16];
-__device__ int g_phase_rounds[64];
-#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+__device__ long long g_phase_last[64];
+#define PHASE_INIT() do { if (threadIdx.x == 0 && blockIdx.x < 64) { for (int q_ = 0; q_ < 16; ++q_) g_phase_clk[blockIdx.x * 16 + q_] = 0; g_phase_last[blockIdx.x] = clock64(); } } while (0)
+#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) { const long long t_ = clock64(); g_phase_clk[blockIdx.x * 16 + (i)] += t_ - g_phase_last[blockIdx.x]; g_phase_last[blockIdx.x] = t_; } } while (0)
+#define PHASE_COUNT(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] += 1; } while (0)
 #else
+#define PHASE_INIT() do { } while (0)
 #define PHASE(i) do { } while (0)
+#define PHASE_COUNT(i) do { } while (0)
 #endif
 __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -943,8 +950,9 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
   u64 lowest = ~0ull;  // lowest generation bound the walk needed (the next call's storing threshold derives from it)
   int walked = 0;
-  PHASE(0);
+  PHASE_INIT();
   while (true) {
+    PHASE(0);  // (setup / bookkeeping between generations)
     // ---- G1: range of the generation from the histogram of cell MAXIMA (an estimate) ----------------
     for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
     __syncthreads();
@@ -969,7 +977,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     const int gen_cells = max(s_res[1], 1);  // cells whose maximum lies in the generation's range
     if (lo_pre >= hi_pre) lo_pre = floor_key;
     __syncthreads();
-    PHASE(1);
+    PHASE(1);  // G1
     // ---- G2: gather [lo_pre, hi_pre) into the list; exact bins --------------------------------------
     int n_list;
     while (true) {
@@ -990,7 +998,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       }
       lo_pre = lo2;
     }
-    PHASE(2);
+    PHASE(2);  // G2
     // ---- G3: chunks of the walk ---------------------------------------------------------------------
     u64 hi = hi_pre;
     // Clustered heatmaps (a real network: ~7 candidates per contributing cell, most of them suppressed by their
@@ -1040,7 +1048,8 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
         __syncthreads();
         bitonic_sort_desc(keys, n_pad);
       }
-      PHASE(3);
+      PHASE(3);  // chunk selection + sort
+      PHASE_COUNT(12);
       whole = false;
       walked += n;
     for (int i = tid; i <= cells; i += kDetectThreads) head[i] = 0;
@@ -1093,7 +1102,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       __syncthreads();
     }
 
-    PHASE(4);
+    PHASE(4);  // A: hash
     // ---- B: fixed-point rounds ---------------------------------------------------------------------
     if (d == 0) {
       for (int i = tid; i < n; i += kDetectThreads)
@@ -1104,6 +1113,10 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       // intra-round data race; the two byte arrays swap roles after each barrier.
       uint8_t* st_in = state;
       uint8_t* st_out = state + cap;
+      // In the FIRST round nobody is decided yet (apart from candidates suppressed by earlier chunks, which are not in
+      // the hash): a candidate with any earlier-rank candidate in its box stays undecided, whatever else is around it,
+      // so its scan may stop at the first one it meets -- in a blob of a real heatmap that is almost immediately.
+      bool first_round = true;
       while (true) {
         int undecided = 0;
         for (int i = tid; i < n; i += kDetectThreads) {
@@ -1115,20 +1128,41 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
             const int cx0 = max(x - d, 0) >> 3, cx1 = min(x + d, W - 1) >> 3;
             const int cy0 = max(y - d, 0) >> 3, cy1 = min(y + d, H - 1) >> 3;
             bool kept = false, undec = false;
-            for (int cy = cy0; cy <= cy1 && !kept; ++cy) {
-              // the cells cx0 .. cx1 of one cell row are adjacent in the counting sort: one contiguous range
-              const int k1 = head[cy * Wc + cx1 + 1];
-              for (int k = head[cy * Wc + cx0]; k < k1; ++k) {
-                const int q = next[k];
-                if (q < i) {
-                  const uint32_t qxy = (uint32_t)keys[q];
-                  const int qx = qxy & 0xFFFF, qy = qxy >> 16;
-                  if (abs(qx - x) <= d && abs(qy - y) <= d) {
-                    const uint8_t sq = st_in[q];
-                    kept |= sq == ST_KEPT;
-                    undec |= sq == ST_UNDEC;
-                  }
+            // The round's time is its slowest thread's, and a neighbour costs a chain of three dependent shared loads
+            // (next -> keys -> state): walk the runs FOUR neighbours at a time so that the chains overlap.
+            auto scan4 = [&](int k, int k1) {  // candidates next[k .. min(k + 4, k1))
+              int q[4];
+              uint32_t qxy[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) q[u] = k + u < k1 ? (int)next[k + u] : 0x7FFFFFFF;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) qxy[u] = q[u] < i ? (uint32_t)keys[q[u]] : 0u;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int qx = qxy[u] & 0xFFFF, qy = qxy[u] >> 16;
+                if (q[u] < i && abs(qx - x) <= d && abs(qy - y) <= d) {
+                  const uint8_t sq = st_in[q[u]];
+                  kept |= sq == ST_KEPT;
+                  undec |= sq == ST_UNDEC;
                 }
+              }
+            };
+            // the cells cx0 .. cx1 of one cell row are adjacent in the counting sort: one contiguous range per row
+            if (cy1 - cy0 <= 2) {  // d <= 8: at most three cell rows, whose six bounds are fetched together
+              int k0[3], len[3];
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const int cy = min(cy0 + r, cy1);
+                k0[r] = head[cy * Wc + cx0];
+                len[r] = cy0 + r <= cy1 ? head[cy * Wc + cx1 + 1] - k0[r] : 0;
+              }
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < len[r] && !kept && !(first_round && undec); k += 4) scan4(k0[r] + k, k0[r] + len[r]);
+            } else {
+              for (int cy = cy0; cy <= cy1 && !kept; ++cy) {
+                const int k1 = head[cy * Wc + cx1 + 1];
+                for (int k = head[cy * Wc + cx0]; k < k1 && !kept && !(first_round && undec); k += 4) scan4(k, k1);
               }
             }
             if (kept) so = ST_SUPP;
@@ -1138,9 +1172,12 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
           st_out[i] = so;
         }
         const int remaining = __syncthreads_count(undecided > 0);
+        PHASE_COUNT(13);
         uint8_t* t = st_in;
         st_in = st_out;
         st_out = t;
+        if (first_round) PHASE(10); else PHASE(11);
+        first_round = false;
         if (remaining == 0) break;
       }
       if (st_in != state) {  // final states must end up in state[]
@@ -1149,7 +1186,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       }
     }
 
-    PHASE(5);
+    PHASE(5);  // B: NMS rounds
     // ---- C: emit kept in-border candidates in rank order, up to K ------------------------------------
     {
       const int seg = (n + kDetectThreads - 1) / kDetectThreads;
@@ -1187,6 +1224,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       if (tid == 0) s_emitted = min(K, s_emitted + total);
       __syncthreads();
     }
+      PHASE(6);  // C: emit
       const bool list_done = lo <= lo_pre;  // this chunk took the rest of the generation's list
       if (s_emitted >= K || (list_done && lo_pre <= floor_key)) {
         done = true;
@@ -1212,6 +1250,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
           }
       }
       __syncthreads();
+      PHASE(7);  // D: bitmap of this chunk's boxes
       hi = lo;
       if (list_done) break;  // next generation: gather the candidates below lo_pre
       bfrom = bto + 1;
@@ -1227,7 +1266,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     hi_pre = lo_pre;
   }
 
-  PHASE(6);
+  PHASE(8);  // D + loop bookkeeping of the last chunk
   // ---- outputs ---------------------------------------------------------------------------------
   const int n_emit = min(s_emitted, K);
   spvo_keypoint* kp = p.kpts + (size_t)b * K;
@@ -1264,7 +1303,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       p.kp_par[(size_t)b * K + i] = par;
     }
   }
-  PHASE(7);
+  PHASE(9);  // outputs
   if (tid == 0) {
     p.n_out[b] = n_emit;
     if (slow) atomicAdd(&p.counters[0], 1ull);
