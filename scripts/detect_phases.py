@@ -38,6 +38,6 @@ a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
 names = ["between", "G1 cell-max histogram", "G2 gather", "chunk select+sort", "A hash", "B NMS rounds", "C emit", "D bitmap",
          "tail", "outputs"]
 for b in range(min(2 * F, 4)):
-    tot = int(a[b, :12].sum())
+    tot = int(a[b, :12].sum() + a[b, 14] + a[b, 15])
     print(f"image {b}: total {tot} clk, {int(a[b, 12])} chunks, {int(a[b, 13])} NMS rounds:  " +
-          "  ".join(f"{n}: {int(x)}" for n, x in zip(names, a[b, :10])) + f"  [NMS first rounds: {int(a[b, 10])}, later rounds: {int(a[b, 11])}]")
+          "  ".join(f"{n}: {int(x)}" for n, x in zip(names, a[b, :10])) + f"  [NMS first rounds: {int(a[b, 10])}, later rounds: {int(a[b, 11])}; gather: stored cells {int(a[b, 14])}, recomputed cells {int(a[b, 15])}]")

@@ -230,6 +230,20 @@ __device__ __forceinline__ u64 make_key(uint32_t bits, int x, int y, int H) {
   return ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
 }
 
+#ifdef SPVO_PHASE_TIMING
+// Diagnostic build only (scripts/build_diag.sh): cycles spent in each phase of k_detect, accumulated over the chunks and
+// generations of one launch, for the first 64 images.  PHASE(i) closes the interval since the previous PHASE and adds
+// it to slot i.
+__device__ long long g_phase_clk[64 * 16];
+__device__ long long g_phase_last[64];
+#define PHASE_INIT() do { if (threadIdx.x == 0 && blockIdx.x < 64) { for (int q_ = 0; q_ < 16; ++q_) g_phase_clk[blockIdx.x * 16 + q_] = 0; g_phase_last[blockIdx.x] = clock64(); } } while (0)
+#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) { const long long t_ = clock64(); g_phase_clk[blockIdx.x * 16 + (i)] += t_ - g_phase_last[blockIdx.x]; g_phase_last[blockIdx.x] = t_; } } while (0)
+#define PHASE_COUNT(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] += 1; } while (0)
+#else
+#define PHASE_INIT() do { } while (0)
+#define PHASE(i) do { } while (0)
+#define PHASE_COUNT(i) do { } while (0)
+#endif
 // The detector logits of one image, [65][cells], fp32 or fp16.
 struct SemiView {
   const void* base;
@@ -522,8 +536,11 @@ __device__ int collect_to_list(const SemiView& sv, const float* __restrict__ hea
     const int ncell = *s_ncell, ncell2 = *s_ncell2;
     __syncthreads();
     if (ncell + ncell2 + kPU * kDetectThreads > cl_cap || c0 + kPU * kDetectThreads >= cells) {
+      PHASE(2);  // G2: records
       fetch_spilled_cells(heat, H, W, conf_bits, lo, hi, cell_list, ncell, list, list_cap, bins, s_count);
+      PHASE(14);  // G2: stored cells
       fetch_listed_cells(sv, H, conf_bits, lo, hi, cell_list + cl_cap - ncell2, ncell2, list, list_cap, bins, s_count, stage);
+      PHASE(15);  // G2: recomputed cells
       __syncthreads();
       if (threadIdx.x == 0) {
         *s_ncell = 0;
@@ -884,20 +901,6 @@ __device__ __forceinline__ u64 bin_to_lo_key(int bin, u64 floor_key) {
 enum : uint8_t { ST_UNDEC = 0, ST_KEPT = 1, ST_SUPP = 2 };
 constexpr uint16_t kNil = 0xFFFFu;
 
-#ifdef SPVO_PHASE_TIMING
-// Diagnostic build only (scripts/build_diag.sh): cycles spent in each phase of k_detect, accumulated over the chunks and
-// generations of one launch, for the first 64 images.  PHASE(i) closes the interval since the previous PHASE and adds
-// it to slot i.
-__device__ long long g_phase_clk[64 * 16];
-__device__ long long g_phase_last[64];
-#define PHASE_INIT() do { if (threadIdx.x == 0 && blockIdx.x < 64) { for (int q_ = 0; q_ < 16; ++q_) g_phase_clk[blockIdx.x * 16 + q_] = 0; g_phase_last[blockIdx.x] = clock64(); } } while (0)
-#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) { const long long t_ = clock64(); g_phase_clk[blockIdx.x * 16 + (i)] += t_ - g_phase_last[blockIdx.x]; g_phase_last[blockIdx.x] = t_; } } while (0)
-#define PHASE_COUNT(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] += 1; } while (0)
-#else
-#define PHASE_INIT() do { } while (0)
-#define PHASE(i) do { } while (0)
-#define PHASE_COUNT(i) do { } while (0)
-#endif
 __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   chain_enter();
@@ -1176,6 +1179,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
         uint8_t* t = st_in;
         st_in = st_out;
         st_out = t;
+        if (first_round) PHASE(10); else PHASE(11);
         if (first_round) PHASE(10); else PHASE(11);
         first_round = false;
         if (remaining == 0) break;
