@@ -40,8 +40,8 @@ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 //     an output of the path, and k_detect only ever needs the pixels of the cells that hold two or more candidates.
 //     A cell's record is its largest and second largest heat value: RN(e / denom) is monotone in e, so they are the
 //     quotients of the two largest exponentials -- two divisions per cell instead of 64.  The 64 heat values are
-//     stored only for cells whose second value reaches a per-image-slot threshold that k_detect left behind on its
-//     previous call (0.9 x the lowest score bound its walk needed): a PREDICTION of the cells it will open.  A
+//     stored only for cells whose second value reaches a per-image-slot threshold derived from what k_detect left
+//     behind on its previous call (0.85 x the score of its K-th keypoint): a PREDICTION of the cells it will open.  A
 //     wrong prediction costs time, never correctness: k_detect recomputes any unstored cell it needs from the
 //     logits (visit_cells, same arithmetic), 65 scattered sectors instead of 8.
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +116,15 @@ __device__ __forceinline__ void store_heat_cells(unsigned marked, const T* __res
   }
 }
 
+// Per image slot the handle remembers ONE number between calls: the score of the K-th keypoint k_detect emitted last
+// time (the confidence threshold if it found fewer than K).  Both predictions derive from it -- a measured property of
+// the previous image, so there is no feedback: cells are stored when their second value reaches 0.85 x it, and
+// k_detect's first generation gathers the candidates above 0.95 x it instead of estimating a bound from the
+// histogram of cell maxima.
+__device__ __forceinline__ uint32_t store_threshold(uint32_t needed_bits) {
+  return fbits(__fmul_rn(0.85f, __uint_as_float(needed_bits)));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kHeatThreads, 4)
 k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __restrict__ cellmax,
@@ -156,7 +165,7 @@ k_softmax_heat(const T* __restrict__ semi, float* __restrict__ heat, uint2* __re
     const float p1 = __fdiv_rn(m1, denom), p2 = __fdiv_rn(m2, denom);
     const uint2 rec = make_uint2(fbits(p1), (fbits(p2) & ~63u) | (uint32_t)arg);
     cellmax[(size_t)b * cells + cell] = rec;
-    store = cell_spilled(rec.y, __ldg(spill_thr + b0 + b), conf_bits);
+    store = cell_spilled(rec.y, store_threshold(__ldg(spill_thr + b0 + b)), conf_bits);
   }
   // Store the 64 heat values of the cells k_detect is expected to open (two or more candidates above the bound its
   // walk reached on this image slot last time).  The logits are re-read (this warp loaded their sectors a moment ago)
@@ -467,13 +476,14 @@ __device__ int collect_to_list(const SemiView& sv, const float* __restrict__ hea
                                const uint2* __restrict__ cellmax, int H, int W,
                                uint32_t conf_bits, u64 lo, u64 hi, u64* __restrict__ list, int list_cap,
                                unsigned* bins, uint16_t* cell_list, int cl_cap, int* s_count, int* s_ncell,
-                               int* s_ncell2, float* stage) {
+                               int* s_ncell2, int* s_gencells, float* stage) {
   const int Wc = W >> 3, cells = (H >> 3) * Wc;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     *s_count = 0;
     *s_ncell = 0;
     *s_ncell2 = 0;
+    *s_gencells = 0;
   }
   __syncthreads();
   const uint32_t lo_b = (uint32_t)(lo >> 32);
@@ -490,6 +500,10 @@ __device__ int collect_to_list(const SemiView& sv, const float* __restrict__ hea
       const int c = c0 + u * kDetectThreads + threadIdx.x;
       const uint32_t mb = rec[u].x;
       const bool q = c < cells && mb > conf_bits && mb >= lo_b && mb < kInfBits;
+      {  // cells whose maximum lies in the range (sizes the first chunk of the walk)
+        const unsigned mq = __ballot_sync(0xffffffffu, q);
+        if (mq && lane == 0) atomicAdd(s_gencells, __popc(mq));
+      }
       const uint32_t sb = rec[u].y | 63u;
       const bool multi = q && sb > conf_bits && sb >= lo_b;
       bool single = q && !multi;
@@ -920,13 +934,14 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   unsigned* s_hist = reinterpret_cast<unsigned*>(keys);          // aliases keys (radix select only)
   unsigned* bins = reinterpret_cast<unsigned*>(state + 2 * cap); // [kHistBins] score-bin histogram (chunk sizing)
   u64* list = p.list + (size_t)b * kListCap;                     // this image's candidate list (global, L2-resident)
-  __shared__ int s_count, s_want, s_emitted, s_ncell2;
+  __shared__ int s_count, s_want, s_emitted, s_ncell2, s_gencells;
   __shared__ int s_res[3];
   __shared__ u64 s_prefix;
   __shared__ unsigned s_warp_tot[kDetectThreads / 32];
 
   const float* heat = p.heat + (size_t)b * H * W;
-  const uint32_t thr_bits = p.spill_thr[b];  // the threshold k_softmax_heat stored cells by on this call
+  const uint32_t needed_prev = p.spill_thr[b];               // score of the K-th keypoint of this slot's previous image
+  const uint32_t thr_bits = store_threshold(needed_prev);    // the threshold k_softmax_heat stored cells by on this call
   SemiView sv;
   sv.base = static_cast<const unsigned char*>(p.semi) + (size_t)b * 65 * cells * (p.semi_f16 ? 2 : 4);
   sv.f16 = p.semi_f16; sv.cells = cells; sv.Wc = Wc; sv.fast_div = p.fast_div;
@@ -951,35 +966,45 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   // heuristic; overflow is detected exactly and repaired, so the result always equals full sort + sequential walk.
   bool slow = false;
   u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
-  u64 lowest = ~0ull;  // lowest generation bound the walk needed (the next call's storing threshold derives from it)
+  bool first_generation = true;
   int walked = 0;
   PHASE_INIT();
   while (true) {
     PHASE(0);  // (setup / bookkeeping between generations)
-    // ---- G1: range of the generation from the histogram of cell MAXIMA (an estimate) ----------------
-    for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
-    __syncthreads();
-    {
-      const uint32_t hi_b = (uint32_t)(hi_pre >> 32);
-      constexpr int kGU = 8;  // records in flight per thread (the loop is a chain of L2 round trips otherwise)
-      for (int c0 = 0; c0 < cells; c0 += kGU * kDetectThreads) {
-        uint32_t mb[kGU];
+    // ---- G1: lower bound of the generation -----------------------------------------------------------
+    // First generation with history: a little below the score of the K-th keypoint this image slot emitted on the
+    // previous call (every multi-candidate cell of that range is a stored one: 0.95 > 0.85).  Otherwise: from the
+    // histogram of the cell MAXIMA (an estimate).  A bound that turns out too high costs another generation, one
+    // too low a longer list -- never the result.
+    u64 lo_pre;
+    if (first_generation && needed_prev > conf_bits && needed_prev <= kOneBits) {
+      const uint32_t gb = fbits(__fmul_rn(0.95f, __uint_as_float(needed_prev)));
+      lo_pre = bin_to_lo_key(score_bin(gb), floor_key);
+    } else {
+      for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
+      __syncthreads();
+      {
+        const uint32_t hi_b = (uint32_t)(hi_pre >> 32);
+        constexpr int kGU = 8;  // records in flight per thread (the loop is a chain of L2 round trips otherwise)
+        for (int c0 = 0; c0 < cells; c0 += kGU * kDetectThreads) {
+          uint32_t mb[kGU];
 #pragma unroll
-        for (int u = 0; u < kGU; ++u) {
-          const int c = c0 + u * kDetectThreads + tid;
-          mb[u] = c < cells ? __ldg(&cellmax[c].x) : 0u;
+          for (int u = 0; u < kGU; ++u) {
+            const int c = c0 + u * kDetectThreads + tid;
+            mb[u] = c < cells ? __ldg(&cellmax[c].x) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < kGU; ++u)
+            if (mb[u] > conf_bits && mb[u] < kInfBits && mb[u] <= hi_b) atomicAdd(&bins[score_bin(mb[u])], 1u);
         }
-#pragma unroll
-        for (int u = 0; u < kGU; ++u)
-          if (mb[u] > conf_bits && mb[u] < kInfBits && mb[u] <= hi_b) atomicAdd(&bins[score_bin(mb[u])], 1u);
       }
+      __syncthreads();
+      pick_bin(bins, 0, p.target, s_warp_tot, s_res);
+      lo_pre = bin_to_lo_key(s_res[0], floor_key);
+      if (lo_pre >= hi_pre) lo_pre = floor_key;
+      __syncthreads();
     }
-    __syncthreads();
-    pick_bin(bins, 0, p.target, s_warp_tot, s_res);
-    u64 lo_pre = bin_to_lo_key(s_res[0], floor_key);
-    const int gen_cells = max(s_res[1], 1);  // cells whose maximum lies in the generation's range
-    if (lo_pre >= hi_pre) lo_pre = floor_key;
-    __syncthreads();
+    first_generation = false;
     PHASE(1);  // G1
     // ---- G2: gather [lo_pre, hi_pre) into the list; exact bins --------------------------------------
     int n_list;
@@ -987,7 +1012,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
       __syncthreads();
       n_list = collect_to_list(sv, heat, thr_bits, cellmax, H, W, conf_bits, lo_pre, hi_pre, list, kListCap, bins, next,
-                               cap, &s_count, &s_want, &s_ncell2, stage);
+                               cap, &s_count, &s_want, &s_ncell2, &s_gencells, stage);
       __syncthreads();
       if (n_list <= kListCap) break;
       slow = true;  // more candidates than the list holds: raise the lower bound exactly and gather again
@@ -1003,6 +1028,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     }
     PHASE(2);  // G2
     // ---- G3: chunks of the walk ---------------------------------------------------------------------
+    const int gen_cells = max(s_gencells, 1);  // cells whose maximum lies in the generation's range (last gather)
     u64 hi = hi_pre;
     // Clustered heatmaps (a real network: ~7 candidates per contributing cell, most of them suppressed by their
     // blob's peak) need a walk several times longer than K: size the first chunk by the observed candidates per cell
@@ -1265,7 +1291,6 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512), max(512LL, need + need / 4 + 128));
       __syncthreads();
     }
-    lowest = lo_pre;
     if (done) break;
     hi_pre = lo_pre;
   }
@@ -1311,8 +1336,9 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   if (tid == 0) {
     p.n_out[b] = n_emit;
     if (slow) atomicAdd(&p.counters[0], 1ull);
-    // next call on this image slot: store the cells whose second value reaches 0.9 x the lowest bound needed now
-    p.spill_thr[b] = fbits(__fmul_rn(0.9f, __uint_as_float((uint32_t)(lowest >> 32))));
+    // for the next call on this image slot (store_threshold): the score of the K-th keypoint, or the confidence
+    // threshold when the image yields fewer than K
+    p.spill_thr[b] = n_emit >= K ? (uint32_t)(emit[K - 1] >> 32) : conf_bits;
   }
 }
 
