@@ -41,7 +41,7 @@ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 //     A cell's record is its largest and second largest heat value: RN(e / denom) is monotone in e, so they are the
 //     quotients of the two largest exponentials -- two divisions per cell instead of 64.  The 64 heat values are
 //     stored only for cells whose second value reaches a per-image-slot threshold derived from what k_detect left
-//     behind on its previous call (0.85 x the score of its K-th keypoint): a PREDICTION of the cells it will open.  A
+//     behind on its previous call (0.8 x the score of its K-th keypoint): a PREDICTION of the cells it will open.  A
 //     wrong prediction costs time, never correctness: k_detect recomputes any unstored cell it needs from the
 //     logits (visit_cells, same arithmetic), 65 scattered sectors instead of 8.
 // ------------------------------------------------------------------------------------------------
@@ -118,11 +118,11 @@ __device__ __forceinline__ void store_heat_cells(unsigned marked, const T* __res
 
 // Per image slot the handle remembers ONE number between calls: the score of the K-th keypoint k_detect emitted last
 // time (the confidence threshold if it found fewer than K).  Both predictions derive from it -- a measured property of
-// the previous image, so there is no feedback: cells are stored when their second value reaches 0.85 x it, and
-// k_detect's first generation gathers the candidates above 0.95 x it instead of estimating a bound from the
+// the previous image, so there is no feedback: cells are stored when their second value reaches 0.8 x it, and
+// k_detect's first generation gathers the candidates above 0.9 x it instead of estimating a bound from the
 // histogram of cell maxima.
 __device__ __forceinline__ uint32_t store_threshold(uint32_t needed_bits) {
-  return fbits(__fmul_rn(0.85f, __uint_as_float(needed_bits)));
+  return fbits(__fmul_rn(0.8f, __uint_as_float(needed_bits)));
 }
 
 template <typename T>
@@ -973,12 +973,12 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
     PHASE(0);  // (setup / bookkeeping between generations)
     // ---- G1: lower bound of the generation -----------------------------------------------------------
     // First generation with history: a little below the score of the K-th keypoint this image slot emitted on the
-    // previous call (every multi-candidate cell of that range is a stored one: 0.95 > 0.85).  Otherwise: from the
+    // previous call (every multi-candidate cell of that range is a stored one: 0.9 > 0.8).  Otherwise: from the
     // histogram of the cell MAXIMA (an estimate).  A bound that turns out too high costs another generation, one
     // too low a longer list -- never the result.
     u64 lo_pre;
     if (first_generation && needed_prev > conf_bits && needed_prev <= kOneBits) {
-      const uint32_t gb = fbits(__fmul_rn(0.95f, __uint_as_float(needed_prev)));
+      const uint32_t gb = fbits(__fmul_rn(0.9f, __uint_as_float(needed_prev)));
       lo_pre = bin_to_lo_key(score_bin(gb), floor_key);
     } else {
       for (int i = tid; i < kHistBins; i += kDetectThreads) bins[i] = 0u;
