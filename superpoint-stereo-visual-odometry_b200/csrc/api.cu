@@ -557,9 +557,6 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
   const int carry_slot = h->max_batch;
   TcSink sink;
   if (tensor) CK(tc_prepare_slots(h, h->max_batch + 1, h->max_k, 2 * h->max_batch, &sink));
-  bool sink_filled = false;  // false when decode used the gather form (planes larger than shared memory)
-  CK(launch_decode(h, semi, desc, in_f16, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr,
-                   tensor ? &sink : nullptr, &sink_filled));
   if (2 * F > h->probs_cap) {
     cudaFree(h->probs);
     h->probs = nullptr;
@@ -568,8 +565,23 @@ static int stereo_pipeline(Handle* h, const void* semi, const void* desc, int in
     h->probs_cap = 2 * F;
   }
   const bool band = (cfg->match.flags & SPVO_MATCH_FLAG_ROW_BAND) != 0;  // L<->R under the row band (opt-in)
-  CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot, band ? kpts : nullptr,
-                                  band ? cfg->stereo_threshold : -1.0f));
+  // the match problems are built by the decode's last kernel when one launch covers the batch (else by k_setup_*)
+  h->stereo_setup = StereoSetup();
+  h->stereo_setup.probs = h->probs; h->stereo_setup.desc_out = desc_out; h->stereo_setup.n_out = n_kpts;
+  h->stereo_setup.carry_desc = h->carry_desc; h->stereo_setup.carry_n = h->carry_n;
+  h->stereo_setup.F = F; h->stereo_setup.K = K; h->stereo_setup.carry_slot = carry_slot;
+  h->stereo_setup.kpts = band ? kpts : nullptr; h->stereo_setup.band = band ? cfg->stereo_threshold : -1.0f;
+  h->stereo_setup_done = false;
+  bool sink_filled = false;  // false when decode used the gather form (planes larger than shared memory)
+  const cudaError_t dec_rc = launch_decode(h, semi, desc, in_f16, 2 * F, H, W, cfg->decode, kpts, desc_out, n_kpts, nullptr,
+                                           tensor ? &sink : nullptr, &sink_filled);
+  const bool setup_done = h->stereo_setup_done;
+  h->stereo_setup = StereoSetup();  // one-shot
+  h->stereo_setup_done = false;
+  CK(dec_rc);
+  if (!setup_done)
+    CK(launch_setup_stereo_problems(h, h->probs, desc_out, n_kpts, F, K, carry_slot, band ? kpts : nullptr,
+                                    band ? cfg->stereo_threshold : -1.0f));
   const bool ready = tensor && sink_filled;
   if (ready && h->has_prev && !h->carry_tc_valid)
     // the previous batch ran on the exact matcher: convert the carried fp32 descriptors into the carry slot

@@ -50,6 +50,56 @@ __device__ __forceinline__ bool band_allowed(const MatchProblem& pr, int i, int 
   return !pr.qy || fabsf(__fsub_rn(__ldg(pr.qy + (size_t)i * pr.ystride), __ldg(pr.ty + (size_t)j * pr.ystride))) <= pr.band;
 }
 
+// The 2F match problems of a stereo batch (L<->R of frame f = problem f; left_f <-> left_{f-1} = problem F + f, frame
+// 0 against the carried previous left image).  Built by k_setup_stereo_problems, or -- one launch fewer -- by block
+// (0, 0) of k_desc_normalize when one decode launch covers the whole batch (Handle::stereo_setup).
+struct StereoSetup {
+  MatchProblem* probs = nullptr;  // null: nothing to do
+  const float* desc_out = nullptr;
+  const int* n_out = nullptr;
+  const float* carry_desc = nullptr;
+  const int* carry_n = nullptr;
+  int F = 0, K = 0, carry_slot = 0;
+  const spvo_keypoint* kpts = nullptr;  // non-null + band >= 0: the L<->R problems carry the row band
+  float band = -1.0f;
+};
+__device__ __forceinline__ void setup_stereo_problem(const StereoSetup& a, int p) {
+  const int F = a.F, K = a.K;
+  MatchProblem pr;
+  pr.qy = pr.ty = nullptr;
+  pr.ystride = 0;
+  pr.band = -1.0f;
+  if (p < F) {
+    if (a.kpts && a.band >= 0.0f) {  // masked mode: only the L<->R problems carry the row band
+      pr.qy = &a.kpts[(size_t)(2 * p) * K].y;
+      pr.ty = &a.kpts[(size_t)(2 * p + 1) * K].y;
+      pr.ystride = (int)(sizeof(spvo_keypoint) / sizeof(float));
+      pr.band = a.band;
+    }
+    pr.q = a.desc_out + (size_t)(2 * p) * K * SPVO_DESC_DIM;
+    pr.t = a.desc_out + (size_t)(2 * p + 1) * K * SPVO_DESC_DIM;
+    pr.N = a.n_out[2 * p];
+    pr.M = a.n_out[2 * p + 1];
+    pr.a_op = 2 * p;       // operand slot = image index (16-bit rows written by k_desc_normalize)
+    pr.b_op = 2 * p + 1;
+  } else {
+    const int f = p - F;
+    pr.q = a.desc_out + (size_t)(2 * f) * K * SPVO_DESC_DIM;
+    pr.N = a.n_out[2 * f];
+    pr.a_op = 2 * f;
+    if (f > 0) {
+      pr.t = a.desc_out + (size_t)(2 * (f - 1)) * K * SPVO_DESC_DIM;
+      pr.M = a.n_out[2 * (f - 1)];
+      pr.b_op = 2 * (f - 1);
+    } else {
+      pr.t = a.carry_desc;
+      pr.M = *a.carry_n;
+      pr.b_op = a.carry_slot;
+    }
+  }
+  a.probs[p] = pr;
+}
+
 // Where k_desc_normalize additionally writes each image's descriptors for the tensor matcher
 // (bf16 rows + fp32 squared norms + per-slot max norm), so the stereo pipeline needs no k_tc_prep.
 struct TcSink {
@@ -191,6 +241,8 @@ struct Handle {
   cudaEvent_t aux_fork = nullptr;
   int decode_subbatches = 0;  // 0 = automatic
   bool chain_launches = false;  // programmatic dependent launch for this call's kernels (small calls only)
+  StereoSetup stereo_setup;     // set by the stereo pipeline before launch_decode; probs == null otherwise
+  bool stereo_setup_done = false;  // launch_decode built the problems (k_desc_normalize), no k_setup launch needed
   // host-form stereo batches: H2D of the next chunk overlaps compute of the current one
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -1515,8 +1515,10 @@ k_desc_planes(const T* __restrict__ desc, const int4* __restrict__ kp_par, const
 // 32 keypoints per block: [256][K] scratch -> shared [32][257] -> normalised [K][256] rows.
 __global__ void __launch_bounds__(256)
 k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K, int Kp,
-                 TcSink sink) {
+                 TcSink sink, const StereoSetup setup) {
   chain_enter();
+  if (setup.probs && blockIdx.x == 0 && blockIdx.y == 0)  // the stereo batch's match problems (saves a launch)
+    for (int p = threadIdx.x; p < 2 * setup.F; p += blockDim.x) setup_stereo_problem(setup, p);
   __shared__ float s[32][257];
   const int b = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1710,8 +1712,14 @@ static cudaError_t launch_decode_range(Handle* h, const void* semi_v, const void
           sg.opmax += g0;
         }
         LaunchScope ls(h, KID_DESC_NORM);
+        // the stereo pipeline's match problems ride along when this one launch covers the whole batch
+        StereoSetup ss;
+        if (h->stereo_setup.probs && b0 == 0 && g0 == 0 && gb == B && B == 2 * h->stereo_setup.F) {
+          ss = h->stereo_setup;
+          h->stereo_setup_done = true;
+        }
         if ((e = launch_chained(h->chain_launches, k_desc_normalize, dim3((rows + 31) / 32, gb), dim3(256), 0, st, 1,
-                                tmp + (size_t)g0 * 256 * Kp, n_out + g0, desc_out + (size_t)g0 * K * 256, K, Kp, sg)) !=
+                                tmp + (size_t)g0 * 256 * Kp, n_out + g0, desc_out + (size_t)g0 * K * 256, K, Kp, sg, ss)) !=
             cudaSuccess)
           return e;
       }

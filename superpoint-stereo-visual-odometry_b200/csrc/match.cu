@@ -252,45 +252,10 @@ __global__ void k_setup_problems(MatchProblem* probs, const float* desc_base, co
 
 // Stereo stream problems: p < F stereo (left_f vs right_f); p >= F temporal (left_f vs left_{f-1},
 // or the carried last-left of the previous batch for f = 0; carry_n = 0 means "no previous frame").
-__global__ void k_setup_stereo_problems(MatchProblem* probs, const float* desc_out, const int* n_out,
-                                        const float* carry_desc, const int* carry_n, int F, int K, int carry_slot,
-                                        const spvo_keypoint* kpts, float band) {
+__global__ void k_setup_stereo_problems(const StereoSetup a) {
   chain_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= 2 * F) return;
-  MatchProblem pr;
-  pr.qy = pr.ty = nullptr;
-  pr.ystride = 0;
-  pr.band = -1.0f;
-  if (p < F) {
-    if (kpts && band >= 0.0f) {  // masked mode: only the L<->R problems carry the row band
-      pr.qy = &kpts[(size_t)(2 * p) * K].y;
-      pr.ty = &kpts[(size_t)(2 * p + 1) * K].y;
-      pr.ystride = (int)(sizeof(spvo_keypoint) / sizeof(float));
-      pr.band = band;
-    }
-    pr.q = desc_out + (size_t)(2 * p) * K * kD;
-    pr.t = desc_out + (size_t)(2 * p + 1) * K * kD;
-    pr.N = n_out[2 * p];
-    pr.M = n_out[2 * p + 1];
-    pr.a_op = 2 * p;       // operand slot = image index (bf16 rows written by k_desc_normalize)
-    pr.b_op = 2 * p + 1;
-  } else {
-    const int f = p - F;
-    pr.q = desc_out + (size_t)(2 * f) * K * kD;
-    pr.N = n_out[2 * f];
-    pr.a_op = 2 * f;
-    if (f > 0) {
-      pr.t = desc_out + (size_t)(2 * (f - 1)) * K * kD;
-      pr.M = n_out[2 * (f - 1)];
-      pr.b_op = 2 * (f - 1);
-    } else {
-      pr.t = carry_desc;
-      pr.M = *carry_n;
-      pr.b_op = carry_slot;
-    }
-  }
-  probs[p] = pr;
+  if (p < 2 * a.F) setup_stereo_problem(a, p);
 }
 
 __global__ void k_set_problem(MatchProblem* probs, const float* q, int N, const float* t, int M,
@@ -479,8 +444,11 @@ cudaError_t launch_setup_stereo_problems(Handle* h, MatchProblem* probs, const f
   if (F == 0) return cudaSuccess;
   {
     LaunchScope ls(h, KID_SETUP);
-    const cudaError_t e = launch_chained(h->chain_launches, k_setup_stereo_problems, dim3((2 * F + 127) / 128), dim3(128), 0, h->stream, 1,
-                                         probs, desc_out, n_out, h->carry_desc, h->carry_n, F, K, carry_slot, kpts, band);
+    StereoSetup a;
+    a.probs = probs; a.desc_out = desc_out; a.n_out = n_out; a.carry_desc = h->carry_desc; a.carry_n = h->carry_n;
+    a.F = F; a.K = K; a.carry_slot = carry_slot; a.kpts = kpts; a.band = band;
+    const cudaError_t e = launch_chained(h->chain_launches, k_setup_stereo_problems, dim3((2 * F + 127) / 128), dim3(128), 0,
+                                         h->stream, 1, a);
     if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
