@@ -727,24 +727,42 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap, const MatchProblem* __restri
 // DMatch.distance is filled in later only if the match survives).  Everything else is queued, with its shortlist,
 // for the warp-per-row k_tc_rerank.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rerank_row(const MatchProblem& pr, int p, int dp, bool rev, int i, const Short& sl, int mode,
+                                           float ratio, const float* __restrict__ nrm, const unsigned* __restrict__ opmax,
+                                           int cap, int max_rows, int max_cols, int* __restrict__ row_best,
+                                           float* __restrict__ row_d, int* __restrict__ col_best, int* __restrict__ fb_count,
+                                           int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
+                                           float eps_rel, int unit);
+
 __global__ void __launch_bounds__(256)
 k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float* __restrict__ nrm,
             const unsigned* __restrict__ opmax, const RowRec* __restrict__ row_rec, const ColRec* __restrict__ col_rec,
             int cap, int max_rows, int max_cols, int* __restrict__ row_best, float* __restrict__ row_d,
             int* __restrict__ col_best, int* __restrict__ rr_count, int* __restrict__ rr_list,
-            Short* __restrict__ shortl, float eps_rel, int unit) {
+            Short* __restrict__ shortl, float eps_rel, int unit, int fuse, float ratio, int* __restrict__ fb_count,
+            int* __restrict__ fb_list, unsigned long long* __restrict__ counters) {
   chain_enter();
+  // fuse != 0 (the NN modes): the few rows this block cannot resolve are re-ranked by the block itself right away
+  // (rerank_row, one warp per row) instead of travelling through global memory to a k_tc_rerank launch
+  __shared__ Short s_sl[256];
+  __shared__ int s_row[256];
+  __shared__ int s_n;
   const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
   const bool rev = dp >= P;
   const MatchProblem pr = probs[p];
   const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
   const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= Na) return;
+  if (blockIdx.x * 256 >= Na) return;  // whole block beyond the problem's rows (uniform)
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const bool active = i < Na;
   bool resolved = false;
   int j0 = -1;
   Short sl;
-  if (Nb == 0) {
+  if (!active) {
+    resolved = true;
+  } else if (Nb == 0) {
     resolved = true;
   } else {
     // entries: 32-bit keys (19-bit value << 13) | column -- values rounded DOWN from the records' 20 / 24 bits (covered
@@ -809,7 +827,8 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
     }
   }
   if (resolved) {
-    if (!rev) {
+    if (!active) {
+    } else if (!rev) {
       const size_t o = ((size_t)p * max_rows + i) * 2;
       row_best[o] = j0;
       row_best[o + 1] = -1;
@@ -818,10 +837,21 @@ k_tc_triage(const MatchProblem* __restrict__ probs, int P, int mode, const float
     } else {
       col_best[(size_t)p * max_cols + i] = j0;
     }
+  } else if (fuse) {
+    const int slot = atomicAdd(&s_n, 1);
+    s_row[slot] = i;
+    s_sl[slot] = sl;
   } else {
     const int slot = atomicAdd(&rr_count[dp], 1);
     rr_list[(size_t)dp * cap + slot] = i;
     shortl[(size_t)dp * cap + slot] = sl;
+  }
+  if (fuse) {
+    __syncthreads();
+    const int n = s_n;
+    for (int li = threadIdx.x >> 5; li < n; li += 8)
+      rerank_row(pr, p, dp, rev, s_row[li], s_sl[li], mode, ratio, nrm, opmax, cap, max_rows, max_cols, row_best, row_d,
+                 col_best, fb_count, fb_list, counters, eps_rel, unit);
   }
 }
 
@@ -857,27 +887,23 @@ __device__ __forceinline__ void top2_push(float d, int j, float& b0, int& x0, fl
   }
 }
 
-constexpr int kPending = -2;  // row_best / col_best of a row queued for k_tc_fallback (see k_tc_rerank, k_tc_fill_dist)
+constexpr int kPending = -2;  // row_best / col_best of a row queued for k_tc_fallback (see rerank_row, k_tc_fill_dist)
 
-__global__ void __launch_bounds__(256)
-k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
-            const unsigned* __restrict__ opmax, const Short* __restrict__ shortl, int cap, int max_rows,
-            int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
-            int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
-            float eps_rel, int unit, const int* __restrict__ rr_count, const int* __restrict__ rr_list) {
-  chain_enter();
-  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
-  const bool rev = dp >= P;
-  const MatchProblem pr = probs[p];
+// One queued row of a directed problem, one WARP: exact fp32 distances (OpenCV order) for the listed candidates inside
+// the proved bound; rows whose unlisted columns are not provably outside go to the fallback list.  Called by
+// k_tc_rerank (rows queued through global memory: the kNN mode, where every row is evaluated) and directly by
+// k_tc_triage (the NN modes: the block re-ranks the few rows it could not resolve itself).
+__device__ __forceinline__ void rerank_row(const MatchProblem& pr, int p, int dp, bool rev, int i, const Short& sl, int mode,
+                                           float ratio, const float* __restrict__ nrm, const unsigned* __restrict__ opmax,
+                                           int cap, int max_rows, int max_cols, int* __restrict__ row_best,
+                                           float* __restrict__ row_d, int* __restrict__ col_best, int* __restrict__ fb_count,
+                                           int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
+                                           float eps_rel, int unit) {
   const int Na = rev ? pr.M : pr.N, Nb = rev ? pr.N : pr.M;
   const float* A = rev ? pr.t : pr.q;
   const float* B = rev ? pr.q : pr.t;
   const int a_op = rev ? pr.b_op : pr.a_op, b_op = rev ? pr.a_op : pr.b_op;
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-  const int n_rr = rr_count[dp];
-  // only the rows k_tc_triage queued; a few blocks per directed problem stride over its list
-  for (int li = blockIdx.x * 8 + (threadIdx.x >> 5); li < n_rr; li += gridDim.x * 8) {
-  const int i = rr_list[(size_t)dp * cap + li];
   float b0 = INFINITY, b1 = INFINITY;
   int x0 = INT_MAX, x1 = INT_MAX;
   bool full = false;
@@ -886,7 +912,6 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
   if (Nb > 0) {
     // the row's shortlist as k_tc_triage normalised it: three best approximate values, their columns, and a lower
     // bound on every column that is not listed
-    const Short sl = shortl[(size_t)dp * cap + li];
     const float na = nrm[(size_t)a_op * cap + i];
     const float amax = __uint_as_float(opmax[a_op]), bmax = __uint_as_float(opmax[b_op]);
     const TcScale ts = tc_scale(bmax, amax, unit != 0);
@@ -946,7 +971,7 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
           col_best[(size_t)p * max_cols + i] = kPending;
         }
       }
-      continue;
+      return;
     } else if (nc == 1 && !knn) {
       // the nearest neighbour is proved without evaluating any distance; DMatch.distance is filled in
       // by k_tc_fill_dist only for the matches that survive (marker: negative distance)
@@ -980,6 +1005,24 @@ k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio
       col_best[(size_t)p * max_cols + i] = x0 == INT_MAX ? -1 : x0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_tc_rerank(const MatchProblem* __restrict__ probs, int P, int mode, float ratio, const float* __restrict__ nrm,
+            const unsigned* __restrict__ opmax, const Short* __restrict__ shortl, int cap, int max_rows,
+            int max_cols, int* __restrict__ row_best, float* __restrict__ row_d, int* __restrict__ col_best,
+            int* __restrict__ fb_count, int* __restrict__ fb_list, unsigned long long* __restrict__ counters,
+            float eps_rel, int unit, const int* __restrict__ rr_count, const int* __restrict__ rr_list) {
+  chain_enter();
+  const int dp = blockIdx.y, p = dp < P ? dp : dp - P;
+  const bool rev = dp >= P;
+  const MatchProblem pr = probs[p];
+  const int n_rr = rr_count[dp];
+  // only the rows k_tc_triage queued; a few blocks per directed problem stride over its list
+  for (int li = blockIdx.x * 8 + (threadIdx.x >> 5); li < n_rr; li += gridDim.x * 8) {
+    const Short sl = shortl[(size_t)dp * cap + li];
+    rerank_row(pr, p, dp, rev, rr_list[(size_t)dp * cap + li], sl, mode, ratio, nrm, opmax, cap, max_rows, max_cols, row_best,
+               row_d, col_best, fb_count, fb_list, counters, eps_rel, unit);
   }
 }
 
@@ -1426,14 +1469,18 @@ cudaError_t launch_match_tc(Handle* h, const MatchProblem* probs, int P, int max
                               w->col_rec, cap, make_idesc(w->fp16), n_items, 256u, w->rr_count, 2 * ndir)) != cudaSuccess)
         return e;
     }
+    // NN modes: the triage blocks re-rank their own unresolved rows (one launch fewer); kNN: every row is evaluated,
+    // which wants the wider k_tc_rerank grid
+    const bool fuse_rerank = cfg.mode != SPVO_MATCH_KNN_RATIO;
     {
       LaunchScope ls(h, KID_TC_TRIAGE);
       if ((e = launch_chained(h->chain_launches, k_tc_triage, dim3((cap + 255) / 256, ndir), dim3(256), 0, st, 1, probs, P, (int)cfg.mode,
                               w->nrm, w->opmax, w->row_rec, w->col_rec, cap, mr, mc, h->row_best, h->row_d, h->col_best,
-                              w->rr_count, w->rr_list, w->shortl, eps_rel, unit)) != cudaSuccess)
+                              w->rr_count, w->rr_list, w->shortl, eps_rel, unit, fuse_rerank ? 1 : 0, cfg.ratio, fb_count,
+                              w->fb_list, h->counters)) != cudaSuccess)
         return e;
     }
-    {
+    if (!fuse_rerank) {
       LaunchScope ls(h, KID_TC_RERANK);
       if ((e = launch_chained(h->chain_launches, k_tc_rerank, dim3(cfg.mode == SPVO_MATCH_KNN_RATIO ? (cap / 32 > 4 ? cap / 32 : 4) : 4, ndir),
                               dim3(256), 0, st, 1, probs, P, (int)cfg.mode, cfg.ratio, w->nrm, w->opmax, w->shortl, cap, mr,
