@@ -3,8 +3,8 @@
 #   /usr/local/graft/bin/gpurun --timeout 3600 -- 'bash scripts/collect_evidence.sh'
 # SANITIZE=1 adds the compute-sanitizer passes (memcheck ~1 min, racecheck ~10 min).
 timeout 600 python bench.py > gpurun_out/bench_r02.json 2> gpurun_out/bench_r02.err; echo bench rc=$?
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 77 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; echo launches rc=$?
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_ -s 11 -c 11 -o gpurun_out/prof_r02 -f python scripts/profile_step.py 148 2 > /dev/null 2>&1; echo ncu rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 70 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; echo launches rc=$?
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_ -s 10 -c 10 -o gpurun_out/prof_r02 -f python scripts/profile_step.py 148 2 > /dev/null 2>&1; echo ncu rc=$?
 timeout 300 python scripts/realistic_report.py gpurun_out/realistic_r02.json > /dev/null 2>&1; echo realistic rc=$?
 timeout 600 python scripts/bench_configs.py gpurun_out/configs_r02.json > /dev/null 2>&1; echo configs rc=$?
 if [ -n "$SANITIZE" ]; then

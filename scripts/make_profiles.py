@@ -31,8 +31,8 @@ for r in rows[hi + 1:]:
     a[0] += 1
     a[1] += v
 tot = sum(v[1] for v in agg.values())
-out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 77 : python bench.py --steps 4 --warmup 3",
-       "# = the 7 device-resident steps of the primary metric (11 launches each); cold-cache, serialised: compare SHARES with bench.py's live shares",
+out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 70 : python bench.py --steps 4 --warmup 3",
+       "# = the 7 device-resident steps of the primary metric (10 launches each); cold-cache, serialised: compare SHARES with bench.py's live shares",
        f"{'kernel':24s} {'launches':>8s} {'total_us':>10s} {'us/launch':>10s} {'share':>7s}"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k:24s} {v[0]:8d} {v[1]:10.1f} {v[1] / v[0]:10.1f} {v[1] / tot:7.3f}")
