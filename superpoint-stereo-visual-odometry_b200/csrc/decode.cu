@@ -1517,8 +1517,6 @@ __global__ void __launch_bounds__(256)
 k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, float* __restrict__ out, int K, int Kp,
                  TcSink sink, const StereoSetup setup) {
   chain_enter();
-  if (setup.probs && blockIdx.x == 0 && blockIdx.y == 0)  // the stereo batch's match problems (saves a launch)
-    for (int p = threadIdx.x; p < 2 * setup.F; p += blockDim.x) setup_stereo_problem(setup, p);
   __shared__ float s[32][257];
   const int b = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1592,6 +1590,10 @@ k_desc_normalize(const float* __restrict__ tmp, const int* __restrict__ n_out, f
     }
   }
   if (xb && lane == 0 && smax > 0.f) atomicMax(&sink.opmax[b], __float_as_uint(smax));
+  // the stereo batch's match problems (saves a launch): one block, AFTER its share of the real work -- at the top of
+  // the kernel the same lines cost every block 20 % (they kept the first loads from being hoisted)
+  if (setup.probs && blockIdx.x == 0 && blockIdx.y == 0)
+    for (int p = threadIdx.x; p < 2 * setup.F; p += blockDim.x) setup_stereo_problem(setup, p);
 }
 
 // ------------------------------------------------------------------------------------------------
