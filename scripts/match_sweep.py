@@ -1,7 +1,7 @@
 """Where does the tensor-core matcher overtake the exact fp32 matcher?  (spvo_match_cfg.algorithm = AUTO is tuned from
 this table: api.cu pick_algorithm.)  Two regimes:
   single   one problem per call (spvo_match_device), N = M
-  batched  148 stereo pairs per call through spvo_stereo_batch_device (296 + 148 problems), K keypoints per image
+  batched  148 stereo pairs per call through spvo_stereo_batch_device (148 + 148 problems), K keypoints per image
 usage: python scripts/match_sweep.py [out.json]
 """
 import json

@@ -343,7 +343,7 @@ static int pick_algorithm(const spvo_match_cfg* cfg, int max_rows, int max_cols,
   // (~35 us for one small problem, flat up to N ~ 1000) and then ~1 ps per pair; the exact fp32 path two to three
   // launches (~19 us) and 45 ps (NN, ratio) to 77 ps (cross-check) per pair while a single problem cannot fill the
   // GPU, ~15 ps per pair in a large batch.  Cross-overs: one problem of N = M = 384 (cross-check), ~576 (NN), ~640
-  // (ratio test); 444 problems (148 stereo pairs) of 64 keypoints.
+  // (ratio test); 296 problems (148 stereo pairs) of 64 keypoints.
   int alg = cfg->algorithm;
   if (alg == SPVO_MATCHER_AUTO) {
     const long long pairs = (long long)max_rows * max_cols;
