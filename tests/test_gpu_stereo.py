@@ -185,3 +185,40 @@ def test_graph_mode_replays_identically(spvo):
         for k in a:
             assert a[k].tobytes() == b[k].tobytes(), (f, k)
     assert plain[3]["n_matches"][1] > 50 and plain[9]["n_matches"][1] == 0  # temporal matches; none right after a reset
+
+
+def test_graph_mode_batches_over_a_ring_of_inputs(spvo):
+    """bench.py's shape in small: batches cycling through a ring of input buffers (several call signatures, both carry
+    parities) replayed as library-owned graphs must reproduce the plain-launch sequence bit for bit, including the
+    concurrent fallback / distance-fill branch and the per-slot detection history."""
+    import torch
+    import spvo_b200.synth as synth
+    S = spvo
+    H, W, K, F, R, NB = 192, 640, 500, 6, 3, 16
+    dev = torch.device("cuda", 0)
+    semi, desc = synth.make_stream(R * F, H, W, seed=21, device=dev)
+    semi = semi.view(R, F, 2, 65, H // 8, W // 8)
+    desc = desc.view(R, F, 2, 256, H // 8, W // 8)
+    kw = dict(max_keypoints=K, mode=1, stereo_threshold=2.0, min_disparity=0.25, algorithm=S.MATCHER_TENSOR)
+
+    def run(graph):
+        fe = S.Frontend(0, 2 * F, H, W, K)
+        fe.set_stream(torch.cuda.current_stream().cuda_stream)
+        fe.set_graph_mode(graph)
+        out = fe.alloc_stereo_out(F, K, device=dev)
+        res = []
+        for b in range(NB):
+            fe.stereo_batch_device(semi[b % R], desc[b % R], F, H, W, out, **kw)
+            torch.cuda.synchronize()
+            res.append({k: v.cpu().numpy().copy() for k, v in out.items()})
+        launches = fe.kernel_launches
+        fe.close()
+        return res, launches
+
+    plain, l0 = run(False)
+    graph, l1 = run(True)
+    assert l0 == l1
+    for b, (a, g) in enumerate(zip(plain, graph)):
+        for k in a:
+            assert a[k].tobytes() == g[k].tobytes(), (b, k)
+    assert plain[-1]["n_matches"].min() > 50
