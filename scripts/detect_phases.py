@@ -32,12 +32,12 @@ for _ in range(4):
     fe.stereo_batch_device(semi, desc, F, H, W, out, max_keypoints=K, mode=S.MATCH_NN_CROSSCHECK)
 torch.cuda.synchronize()
 lib = ctypes.CDLL(diag)
-buf = (ctypes.c_longlong * (64 * 16))()
+buf = (ctypes.c_longlong * (64 * 32))()
 assert lib.spvo_debug_phase_clocks(buf) == 0
-a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
+a = np.array(buf[:], dtype=np.int64).reshape(64, 32)
 names = ["between", "G1 cell-max histogram", "G2 gather", "chunk select+sort", "A hash", "B NMS rounds", "C emit", "D bitmap",
          "tail", "outputs"]
 for b in range(min(2 * F, 4)):
     tot = int(a[b, :12].sum() + a[b, 14] + a[b, 15])
     print(f"image {b}: total {tot} clk, {int(a[b, 12])} chunks, {int(a[b, 13])} NMS rounds:  " +
-          "  ".join(f"{n}: {int(x)}" for n, x in zip(names, a[b, :10])) + f"  [NMS first rounds: {int(a[b, 10])}, later rounds: {int(a[b, 11])}; gather: stored cells {int(a[b, 14])}, recomputed cells {int(a[b, 15])}]")
+          "  ".join(f"{n}: {int(x)}" for n, x in zip(names, a[b, :10])) + f"  [NMS first rounds: {int(a[b, 10])}, later rounds: {int(a[b, 11])}; gather: stored cells {int(a[b, 14])}, recomputed cells {int(a[b, 15])}]  chunk sizes {[int(x) for x in a[b, 16:23] if x]} emitted after each {[int(x) for x in a[b, 24:31] if x]}")

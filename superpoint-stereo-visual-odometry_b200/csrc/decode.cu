@@ -208,7 +208,7 @@ cudaError_t launch_div_check(Handle* h, const uint32_t* a_bits, const uint32_t* 
 // ------------------------------------------------------------------------------------------------
 struct DetectParams {
   const float* heat;     // [B, H, W] heat values of the cells k_softmax_heat chose to store (cell_spilled)
-  uint32_t* spill_thr;   // [B] per image slot: threshold k_softmax_heat used; rewritten for the next call
+  uint32_t* spill_thr;   // [B] per image slot: score bits of the K-th keypoint of the previous call; rewritten for the next
   const void* semi;      // [B, 65, cells] detector logits (fp32 or fp16): other multi-candidate cells are recomputed
   int semi_f16;
   int fast_div;          // shared-reciprocal division allowed (conf_thresh >= 1e-20)
@@ -243,15 +243,19 @@ __device__ __forceinline__ u64 make_key(uint32_t bits, int x, int y, int H) {
 // Diagnostic build only (scripts/build_diag.sh): cycles spent in each phase of k_detect, accumulated over the chunks and
 // generations of one launch, for the first 64 images.  PHASE(i) closes the interval since the previous PHASE and adds
 // it to slot i.
-__device__ long long g_phase_clk[64 * 16];
+__device__ long long g_phase_clk[64 * 32];
 __device__ long long g_phase_last[64];
-#define PHASE_INIT() do { if (threadIdx.x == 0 && blockIdx.x < 64) { for (int q_ = 0; q_ < 16; ++q_) g_phase_clk[blockIdx.x * 16 + q_] = 0; g_phase_last[blockIdx.x] = clock64(); } } while (0)
-#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) { const long long t_ = clock64(); g_phase_clk[blockIdx.x * 16 + (i)] += t_ - g_phase_last[blockIdx.x]; g_phase_last[blockIdx.x] = t_; } } while (0)
-#define PHASE_COUNT(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 16 + (i)] += 1; } while (0)
+#define g_phase_clk_chunks() (blockIdx.x < 64 ? g_phase_clk[blockIdx.x * 32 + 12] : 0)
+#define PHASE_INIT() do { if (threadIdx.x == 0 && blockIdx.x < 64) { for (int q_ = 0; q_ < 32; ++q_) g_phase_clk[blockIdx.x * 32 + q_] = 0; g_phase_last[blockIdx.x] = clock64(); } } while (0)
+#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) { const long long t_ = clock64(); g_phase_clk[blockIdx.x * 32 + (i)] += t_ - g_phase_last[blockIdx.x]; g_phase_last[blockIdx.x] = t_; } } while (0)
+#define PHASE_COUNT(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_phase_clk[blockIdx.x * 32 + (i)] += 1; } while (0)
+#define PHASE_NOTE(i, v) do { if (threadIdx.x == 0 && blockIdx.x < 64 && (i) < 32) g_phase_clk[blockIdx.x * 32 + (i)] = (v); } while (0)
 #else
 #define PHASE_INIT() do { } while (0)
 #define PHASE(i) do { } while (0)
 #define PHASE_COUNT(i) do { } while (0)
+#define PHASE_NOTE(i, v) do { } while (0)
+#define g_phase_clk_chunks() 0
 #endif
 // The detector logits of one image, [65][cells], fp32 or fp16.
 struct SemiView {
@@ -967,7 +971,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
   bool slow = false;
   u64 hi_pre = ~0ull;  // every candidate >= hi_pre has been consumed
   bool first_generation = true;
-  int walked = 0;
+  int emitted_before = 0;  // s_emitted at the start of the current chunk (marginal emission rate)
   PHASE_INIT();
   while (true) {
     PHASE(0);  // (setup / bookkeeping between generations)
@@ -1078,9 +1082,9 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
         bitonic_sort_desc(keys, n_pad);
       }
       PHASE(3);  // chunk selection + sort
+      PHASE_NOTE(16 + (int)g_phase_clk_chunks(), n);
       PHASE_COUNT(12);
       whole = false;
-      walked += n;
     for (int i = tid; i <= cells; i += kDetectThreads) head[i] = 0;
     __syncthreads();
 
@@ -1255,6 +1259,7 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       __syncthreads();
     }
       PHASE(6);  // C: emit
+      PHASE_NOTE(23 + (int)g_phase_clk_chunks(), s_emitted);
       const bool list_done = lo <= lo_pre;  // this chunk took the rest of the generation's list
       if (s_emitted >= K || (list_done && lo_pre <= floor_key)) {
         done = true;
@@ -1284,11 +1289,14 @@ __global__ void __launch_bounds__(kDetectThreads, 2) k_detect(DetectParams p) {
       hi = lo;
       if (list_done) break;  // next generation: gather the candidates below lo_pre
       bfrom = bto + 1;
-      // size the next chunk from what the walk has yielded so far: (K - emitted) more keypoints at the observed
-      // emission rate, with a margin; bounded by the buffer
-      const int em = max(s_emitted, 1);
-      const long long need = (long long)(K - s_emitted) * walked / em;
-      chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512), max(512LL, need + need / 4 + 128));
+      // size the next chunk from what the LAST chunk yielded: (K - emitted) more keypoints at its emission rate -- the
+      // marginal rate, which keeps falling on clustered heatmaps (real outputs: 28 % -> 10 % -> 9 % -> 7 % per chunk:
+      // lower-scored candidates are more often inside an earlier keypoint's box), so the average over the whole walk
+      // undersizes every chunk -- with a margin; bounded by the buffer
+      const int d_em = max(s_emitted - emitted_before, 1);
+      const long long need = (long long)(K - s_emitted) * n / d_em;
+      chunk_target = (int)min((long long)min(cap * 3 / 4, kBucketMax - 512), max(512LL, need + need / 2 + 128));
+      emitted_before = s_emitted;
       __syncthreads();
     }
     if (done) break;
@@ -1778,6 +1786,6 @@ size_t decode_list_bytes_per_image() { return (size_t)kListCap * sizeof(u64); }
 
 #ifdef SPVO_PHASE_TIMING
 extern "C" int spvo_debug_phase_clocks(long long* out) {  // [64][16] clock64 stamps of k_detect's phases; diagnostic builds only
-  return cudaMemcpyFromSymbol(out, spvo::g_phase_clk, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, spvo::g_phase_clk, sizeof(long long) * 64 * 32) == cudaSuccess ? 0 : -1;
 }
 #endif
